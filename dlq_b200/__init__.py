@@ -1,0 +1,337 @@
+"""dlq_b200 — host-side Python mirror of the libdlq_b200.so C ABI (include/dlq.h).
+
+The product is the CUDA library; this module only binds it with ctypes so that tests and bench.py can
+drive it with torch tensors as device memory.  There is NO CPU fallback: importing works without a
+GPU (so the ABI can be inspected), but creating a Context without the library or without a B200
+raises.
+
+Reference surface mirrored here (yeontachi/DLQ, CUDA/resnet18-kernel-lab/cpp/fp32):
+  conv2d_nchw_im2col_gemm   runtime/infer_e2e.cu:102-136   -> Context.conv2d_i8
+  bn_launch / bn_inference  runtime/infer_e2e.cu:83-97     -> Context.bn_inference_f32 (standalone) / folded
+  relu_forward, add_inplace kernels/relu.cu, kernels/add.cu
+  maxpool2d_3x3_s2p1_nchw   kernels/maxpool2d.cu:5-41
+  gap_global, fc_forward    kernels/gap_global.cu, runtime/infer_e2e.cu:206-219
+  main() wiring             runtime/infer_e2e.cu:254-433   -> ResNet18.forward
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdlq_b200.so")
+
+NUM_CONVS = 25
+NUM_ACTS = 27
+ACT_INPUT, ACT_STEM, ACT_GAP = 0, 1, 26
+
+# every symbol include/dlq.h declares (checked by tests/test_abi.py against the header and the .so)
+ABI_SYMBOLS = [
+    "dlq_create", "dlq_destroy", "dlq_last_error_string", "dlq_sync", "dlq_stream", "dlq_set_stream", "dlq_version",
+    "dlq_quantize_f32_i8", "dlq_dequantize_i8_f32", "dlq_dequantize_i8_f32_per_channel",
+    "dlq_conv_weights_pack", "dlq_conv_weights_pack_i8", "dlq_conv_weights_free", "dlq_conv2d_i8",
+    "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
+    "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
+    "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
+    "dlq_resnet18_checkpoint", "dlq_resnet18_launches", "dlq_synth_fill_f32",
+    "dlq_multi_create", "dlq_multi_destroy", "dlq_multi_forward_host", "dlq_multi_last_error_string",
+]
+
+
+class DlqError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dlq error {code}: {msg}")
+        self.code = code
+
+
+class _Epilogue(C.Structure):
+    _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_scale", C.c_float),
+                ("relu", C.c_int), ("out_scale", C.c_float)]
+
+
+class _ResNet18Weights(C.Structure):
+    _fields_ = [("conv_w", C.c_void_p * NUM_CONVS), ("bn_gamma", C.c_void_p * NUM_CONVS),
+                ("bn_beta", C.c_void_p * NUM_CONVS), ("bn_mean", C.c_void_p * NUM_CONVS),
+                ("bn_var", C.c_void_p * NUM_CONVS), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p),
+                ("act_scale", C.c_float * NUM_ACTS)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libdlq_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built; run `make -C dlq_b200/csrc` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "dlq_create": (i, [i, C.POINTER(vp)]),
+        "dlq_destroy": (None, [vp]),
+        "dlq_last_error_string": (C.c_char_p, [vp]),
+        "dlq_sync": (i, [vp]),
+        "dlq_stream": (vp, [vp]),
+        "dlq_set_stream": (i, [vp, vp]),
+        "dlq_version": (C.c_char_p, []),
+        "dlq_quantize_f32_i8": (i, [vp, vp, sz, f, vp]),
+        "dlq_dequantize_i8_f32": (i, [vp, vp, sz, f, vp]),
+        "dlq_dequantize_i8_f32_per_channel": (i, [vp, vp, i, i, i, vp, vp]),
+        "dlq_conv_weights_pack": (i, [vp, vp, i, i, i, i, i, i, i, i, vp, C.POINTER(vp)]),
+        "dlq_conv_weights_pack_i8": (i, [vp, vp, i, i, i, i, i, i, i, i, C.POINTER(vp)]),
+        "dlq_conv_weights_free": (None, [vp]),
+        "dlq_conv2d_i8": (i, [vp, vp, i, i, i, i, vp, C.POINTER(_Epilogue), vp, vp, C.POINTER(i), C.POINTER(i)]),
+        "dlq_bn_inference_f32": (i, [vp, vp, vp, vp, vp, vp, f, i, i, i, i]),
+        "dlq_relu_forward_f32": (i, [vp, vp, sz]),
+        "dlq_relu_forward_i8": (i, [vp, vp, sz]),
+        "dlq_add_inplace_f32": (i, [vp, vp, vp, sz]),
+        "dlq_add_requant_i8": (i, [vp, vp, f, vp, f, sz, i, f]),
+        "dlq_maxpool2d_3x3_s2p1_nchw_i8": (i, [vp, vp, i, i, i, i, vp]),
+        "dlq_gap_global_i8": (i, [vp, vp, i, i, i, i, f, f, vp, vp]),
+        "dlq_fc_forward_i8": (i, [vp, vp, vp, vp, vp, i, i, i, vp]),
+        "dlq_softmax_f32": (i, [vp, vp, i, i, vp]),
+        "dlq_resnet18_create": (i, [vp, C.POINTER(_ResNet18Weights), i, C.POINTER(vp)]),
+        "dlq_resnet18_destroy": (None, [vp]),
+        "dlq_resnet18_forward": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_forward_host": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_checkpoint": (i, [vp, C.c_char_p, vp]),
+        "dlq_resnet18_launches": (i, [vp]),
+        "dlq_synth_fill_f32": (None, [vp, sz, C.c_uint64, C.c_char_p, i, i, i]),
+        "dlq_multi_create": (i, [C.POINTER(i), i, C.POINTER(_ResNet18Weights), i, C.POINTER(vp)]),
+        "dlq_multi_destroy": (None, [vp]),
+        "dlq_multi_forward_host": (i, [vp, vp, i, vp]),
+        "dlq_multi_last_error_string": (C.c_char_p, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(t) -> Optional[int]:
+    """device pointer of a torch tensor (or None)"""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def synth_fill_f32(shape, seed: int, name: str, lo: int, hi: int, shift: int) -> np.ndarray:
+    """Deterministic lattice tensor: (lo + splitmix64(seed,name) % (hi-lo+1)) * 2^-shift."""
+    lib = load_library()
+    a = np.empty(shape, dtype=np.float32)
+    lib.dlq_synth_fill_f32(a.ctypes.data, a.size, seed, name.encode(), lo, hi, shift)
+    return a
+
+
+class ConvWeights:
+    def __init__(self, ctx: "Context", handle: int, scale: Optional[np.ndarray], oc: int):
+        self.ctx, self.handle, self.scale, self.oc = ctx, handle, scale, oc
+
+    def free(self):
+        if self.handle:
+            load_library().dlq_conv_weights_free(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One per device; enqueues on its own stream (see dlq.h)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.dlq_create(device, C.byref(h))
+        if rc != 0:
+            raise DlqError(rc, f"dlq_create(device={device}) failed: no usable sm_100 GPU (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.dlq_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise DlqError(rc, self.lib.dlq_last_error_string(self.h).decode())
+
+    def sync(self):
+        self._ck(self.lib.dlq_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return self.lib.dlq_stream(self.h)
+
+    # ---- quantise / dequantise
+    def quantize_f32_i8(self, x, scale: float, q):
+        self._ck(self.lib.dlq_quantize_f32_i8(self.h, _ptr(x), x.numel(), scale, _ptr(q)))
+
+    def dequantize_i8_f32(self, q, scale: float, x):
+        self._ck(self.lib.dlq_dequantize_i8_f32(self.h, _ptr(q), q.numel(), scale, _ptr(x)))
+
+    def dequantize_i8_f32_per_channel(self, q, scales, x):
+        n, c = q.shape[0], q.shape[1]
+        hw = q.numel() // max(1, n * c)
+        self._ck(self.lib.dlq_dequantize_i8_f32_per_channel(self.h, _ptr(q), n, c, hw, _ptr(scales), _ptr(x)))
+
+    # ---- conv
+    def pack_conv_weights(self, w_oihw: np.ndarray, stride: int, pad: int) -> ConvWeights:
+        w = np.ascontiguousarray(w_oihw, dtype=np.float32)
+        oc, ic, kh, kw = w.shape
+        scale = np.empty(oc, dtype=np.float32)
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_conv_weights_pack(self.h, w.ctypes.data, oc, ic, kh, kw, stride, stride, pad, pad,
+                                                scale.ctypes.data, C.byref(h)))
+        return ConvWeights(self, h, scale, oc)
+
+    def pack_conv_weights_i8(self, wq_oihw: np.ndarray, stride: int, pad: int) -> ConvWeights:
+        w = np.ascontiguousarray(wq_oihw, dtype=np.int8)
+        oc, ic, kh, kw = w.shape
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_conv_weights_pack_i8(self.h, w.ctypes.data, oc, ic, kh, kw, stride, stride, pad, pad,
+                                                   C.byref(h)))
+        return ConvWeights(self, h, None, oc)
+
+    def conv2d_i8(self, x, w: ConvWeights, alpha=None, beta=None, residual=None, res_scale: float = 0.0,
+                  relu: bool = False, out_scale: float = 1.0, y=None, acc_out=None):
+        n, c, hh, ww = x.shape
+        ep = _Epilogue(_ptr(alpha), _ptr(beta), _ptr(residual), res_scale, int(relu), out_scale)
+        oh, ow = C.c_int(), C.c_int()
+        self._ck(self.lib.dlq_conv2d_i8(self.h, _ptr(x), n, c, hh, ww, w.handle,
+                                        C.byref(ep) if alpha is not None else None, _ptr(y), _ptr(acc_out),
+                                        C.byref(oh), C.byref(ow)))
+        return oh.value, ow.value
+
+    # ---- element-wise / pooling
+    def bn_inference_f32(self, x, g, b, m, v, eps: float = 1e-5):
+        n, c, oh, ow = x.shape
+        self._ck(self.lib.dlq_bn_inference_f32(self.h, _ptr(x), _ptr(g), _ptr(b), _ptr(m), _ptr(v), eps, n, c, oh, ow))
+
+    def relu_forward_f32(self, x):
+        self._ck(self.lib.dlq_relu_forward_f32(self.h, _ptr(x), x.numel()))
+
+    def relu_forward_i8(self, x):
+        self._ck(self.lib.dlq_relu_forward_i8(self.h, _ptr(x), x.numel()))
+
+    def add_inplace_f32(self, y, x):
+        self._ck(self.lib.dlq_add_inplace_f32(self.h, _ptr(y), _ptr(x), y.numel()))
+
+    def add_requant_i8(self, y, y_scale, x, x_scale, relu, out_scale):
+        self._ck(self.lib.dlq_add_requant_i8(self.h, _ptr(y), y_scale, _ptr(x), x_scale, y.numel(), int(relu), out_scale))
+
+    def maxpool2d_3x3_s2p1_nchw_i8(self, x, y):
+        n, c, hh, ww = x.shape
+        self._ck(self.lib.dlq_maxpool2d_3x3_s2p1_nchw_i8(self.h, _ptr(x), n, c, hh, ww, _ptr(y)))
+
+    def gap_global_i8(self, x, in_scale, out_scale, y_f32=None, y_i8=None):
+        n, c, hh, ww = x.shape
+        self._ck(self.lib.dlq_gap_global_i8(self.h, _ptr(x), n, c, hh, ww, in_scale, out_scale, _ptr(y_f32), _ptr(y_i8)))
+
+    def fc_forward_i8(self, g, w, scale, bias, logits):
+        n, i = g.shape
+        o = w.shape[0]
+        self._ck(self.lib.dlq_fc_forward_i8(self.h, _ptr(g), _ptr(w), _ptr(scale), _ptr(bias), n, o, i, _ptr(logits)))
+
+    def softmax_f32(self, x, y):
+        n, k = x.shape
+        self._ck(self.lib.dlq_softmax_f32(self.h, _ptr(x), n, k, _ptr(y)))
+
+
+def _weights_struct(weights: Dict[str, np.ndarray], act_scale) -> tuple:
+    """Build the dlq_resnet18_weights struct from a dict keyed like the reference's <key>.bin export
+    (tools/export_resnet18.py:85-92); returns (struct, keepalive list)."""
+    from .synth import conv_keys
+    s = _ResNet18Weights()
+    keep = []
+
+    def put(arr_field, idx, key):
+        a = np.ascontiguousarray(weights[key], dtype=np.float32)
+        keep.append(a)
+        arr_field[idx] = a.ctypes.data
+
+    for idx, (wkey, bnkey) in conv_keys().items():
+        if wkey not in weights:
+            continue
+        put(s.conv_w, idx, wkey)
+        put(s.bn_gamma, idx, bnkey + ".weight")
+        put(s.bn_beta, idx, bnkey + ".bias")
+        put(s.bn_mean, idx, bnkey + ".running_mean")
+        put(s.bn_var, idx, bnkey + ".running_var")
+    fw = np.ascontiguousarray(weights["fc.weight"], dtype=np.float32)
+    fb = np.ascontiguousarray(weights["fc.bias"], dtype=np.float32)
+    keep += [fw, fb]
+    s.fc_w, s.fc_b = fw.ctypes.data, fb.ctypes.data
+    for i in range(NUM_ACTS):
+        s.act_scale[i] = float(act_scale[i])
+    return s, keep
+
+
+class ResNet18:
+    """Whole-network INT8 runner (replaces main() of runtime/infer_e2e.cu for a batch)."""
+
+    def __init__(self, ctx: Context, weights: Dict[str, np.ndarray], act_scale, max_batch: int):
+        self.ctx = ctx
+        s, keep = _weights_struct(weights, act_scale)
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.dlq_resnet18_create(ctx.h, C.byref(s), max_batch, C.byref(h)))
+        self.h = h
+        self.max_batch = max_batch
+
+    def forward(self, x, logits):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_forward(self.h, _ptr(x), x.shape[0], _ptr(logits)))
+
+    def forward_host(self, x_host, logits_host):
+        """x_host / logits_host: CPU torch tensors (pinned for full speed) or numpy arrays."""
+        xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
+        lp = logits_host.data_ptr() if hasattr(logits_host, "data_ptr") else logits_host.ctypes.data
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_host(self.h, xp, x_host.shape[0], lp))
+
+    def checkpoint(self, name: str, out):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_checkpoint(self.h, name.encode(), _ptr(out)))
+
+    @property
+    def launches(self) -> int:
+        return self.ctx.lib.dlq_resnet18_launches(self.h)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dlq_resnet18_destroy(self.h)
+            self.h = None
+
+
+class MultiGPU:
+    """Batch-sharded driver over several devices of one box (host buffers in, host logits out)."""
+
+    def __init__(self, devices, weights: Dict[str, np.ndarray], act_scale, max_batch_per_device: int):
+        self.lib = load_library()
+        s, keep = _weights_struct(weights, act_scale)
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.dlq_multi_create(devs, len(devices), C.byref(s), max_batch_per_device, C.byref(h))
+        if rc != 0:
+            raise DlqError(rc, "dlq_multi_create failed")
+        self.h = h
+
+    def forward_host(self, x_host, logits_host):
+        xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
+        lp = logits_host.data_ptr() if hasattr(logits_host, "data_ptr") else logits_host.ctypes.data
+        rc = self.lib.dlq_multi_forward_host(self.h, xp, x_host.shape[0], lp)
+        if rc != 0:
+            raise DlqError(rc, self.lib.dlq_multi_last_error_string(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.dlq_multi_destroy(self.h)
+            self.h = None

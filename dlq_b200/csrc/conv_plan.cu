@@ -1,0 +1,339 @@
+// conv_plan.cu — host side of the INT8 convolution: weight packing into shared-memory images,
+// launch planning (virtual position space, sub-patches, K-step schedule, TMA descriptor) and launch.
+//
+// Replaces the per-call host work of conv2d_nchw_im2col_gemm (reference runtime/infer_e2e.cu:102-136:
+// OIHW -> [OC, IC*kH*kW] repack, 3x cudaMalloc, weight upload, two launches) with a pack-once /
+// plan-once / launch-many split.
+#include "dlq_internal.h"
+#include <algorithm>
+
+namespace dlq {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+struct SubDesc {
+  int c0;           // channel byte offset
+  int col0;         // TMA start column
+  int row_off_rel;  // TMA row = row_mul * v0 + PR_in + row_off_rel
+};
+struct StepDesc {
+  int sub;
+  int kh, kw;  // filter tap (stem: kh = row block a, kw = column pair bp)
+  int kb;      // channel block
+  int da, db;  // tap shift in patch rows / columns
+};
+
+void make_schedule(const dlq_conv_weights* w, std::vector<SubDesc>& subs, std::vector<StepDesc>& steps) {
+  subs.clear();
+  steps.clear();
+  const int rowb = w->rowb;
+  switch (w->kind) {
+    case CONV_S1:
+      for (int kb = 0; kb < w->kb; ++kb) {
+        subs.push_back({kb * rowb, -w->pW, -w->pH});
+        for (int kh = 0; kh < w->kH; ++kh)
+          for (int kw = 0; kw < w->kW; ++kw) steps.push_back({kb, kh, kw, kb, kh, kw});
+      }
+      break;
+    case CONV_S2_3x3: {
+      // parity planes of the input (row parity, col parity) and the taps that read them.
+      // input row 2*oh - 1 + kh: kh=0 -> odd plane index oh-1 (da 0), kh=1 -> even plane (da 0),
+      // kh=2 -> odd plane index oh (da 1).  Same for columns.
+      struct Tap { int kh, kw, da, db; };
+      struct Plane { int row_off_rel, col0; std::vector<Tap> taps; };
+      const Plane planes[4] = {
+          {-1, -1, {{0, 0, 0, 0}, {0, 2, 0, 1}, {2, 0, 1, 0}, {2, 2, 1, 1}}},
+          {-1, 0, {{0, 1, 0, 0}, {2, 1, 1, 0}}},
+          {0, -1, {{1, 0, 0, 0}, {1, 2, 0, 1}}},
+          {0, 0, {{1, 1, 0, 0}}},
+      };
+      for (const Plane& pl : planes)
+        for (int kb = 0; kb < w->kb; ++kb) {
+          const int s = static_cast<int>(subs.size());
+          subs.push_back({kb * rowb, pl.col0, pl.row_off_rel});
+          for (const Tap& t : pl.taps) steps.push_back({s, t.kh, t.kw, kb, t.da, t.db});
+        }
+      break;
+    }
+    case CONV_S2_1x1:
+      for (int kb = 0; kb < w->kb; ++kb) {
+        subs.push_back({kb * rowb, 0, 0});
+        steps.push_back({kb, 0, 0, kb, 0, 0});
+      }
+      break;
+    case CONV_STEM:
+      // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 B per pixel):
+      // input row 2*oh - 3 + kh = 2*(oh - 2) + (kh + 1)  ->  s2d row oh - 2 + a, a = (kh+1)/2, dy = (kh+1)%2.
+      subs.push_back({0, -2, -2});
+      for (int a = 0; a < 4; ++a)
+        for (int bp = 0; bp < 2; ++bp) steps.push_back({0, a, bp, 0, a, 2 * bp});
+      break;
+  }
+}
+
+inline uint32_t swz_off(uint32_t row, uint32_t kbyte, uint32_t row_bytes) {
+  const uint32_t lin = row * row_bytes + kbyte;
+  if (row_bytes == 128) return lin ^ (((lin >> 7) & 7u) << 4);
+  if (row_bytes == 64) return lin ^ (((lin >> 7) & 3u) << 4);
+  return lin;
+}
+
+}  // namespace
+
+void conv_out_dims(const dlq_conv_weights* w, int H, int W, int* OH, int* OW) {
+  *OH = (H + 2 * w->pH - w->kH) / w->sH + 1;
+  *OW = (W + 2 * w->pW - w->kW) / w->sW + 1;
+}
+
+int conv_required_in_pr(const dlq_conv_weights* w) {
+  switch (w->kind) {
+    case CONV_S1: return w->pH;
+    case CONV_S2_3x3: return 2;   // >= 1 and H + PR even (H even)
+    case CONV_S2_1x1: return 2;
+    case CONV_STEM: return 2;
+  }
+  return 0;
+}
+
+int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                      int pW, dlq_conv_weights* out) {
+  DLQ_ARG(ctx, OC > 0 && OC % 64 == 0, "OC must be a multiple of 64");
+  DLQ_ARG(ctx, kH == kW && sH == sW && pH == pW, "square kernels / strides / pads only");
+  out->OC = OC; out->IC = IC; out->kH = kH; out->kW = kW; out->sH = sH; out->sW = sW; out->pH = pH; out->pW = pW;
+  out->device = ctx->device;
+  if (IC == 3 && kH == 7 && sH == 2 && pH == 3) {
+    out->kind = CONV_STEM; out->rowb = 16; out->kb = 1;
+  } else {
+    DLQ_ARG(ctx, IC == 64 || (IC > 0 && IC % 128 == 0), "IC must be 64 or a multiple of 128 (or the 3-channel 7x7/s2/p3 stem)");
+    out->rowb = IC == 64 ? 64 : 128;
+    out->kb = IC == 64 ? 1 : IC / 128;
+    if (sH == 1) {
+      DLQ_ARG(ctx, kH >= 1 && kH <= 7 && (kH & 1) && pH <= kH / 2, "stride-1 conv: odd k <= 7, pad <= k/2");
+      out->kind = CONV_S1;
+    } else if (sH == 2 && kH == 3 && pH == 1) {
+      out->kind = CONV_S2_3x3;
+    } else if (sH == 2 && kH == 1 && pH == 0) {
+      out->kind = CONV_S2_1x1;
+    } else {
+      DLQ_ARG(ctx, false, "unsupported (kernel, stride, pad) combination");
+    }
+  }
+  out->n_tile = (OC % 128 == 0) ? 128 : 64;
+  std::vector<SubDesc> subs;
+  std::vector<StepDesc> steps;
+  make_schedule(out, subs, steps);
+  DLQ_ARG(ctx, static_cast<int>(steps.size()) <= kMaxSteps && subs.size() <= 16, "too many K steps for one conv");
+  out->n_steps = static_cast<int>(steps.size());
+  out->step_bytes = out->kind == CONV_STEM ? out->n_tile * 32u : static_cast<uint32_t>(out->n_tile) * out->rowb;
+  out->q_oihw.assign(wq, wq + static_cast<size_t>(OC) * IC * kH * kW);
+
+  const int n_tiles = OC / out->n_tile;
+  std::vector<uint8_t> img(static_cast<size_t>(n_tiles) * out->n_steps * out->step_bytes, 0);
+  auto W = [&](int o, int c, int kh, int kw) -> int8_t {
+    return wq[((static_cast<size_t>(o) * IC + c) * kH + kh) * kW + kw];
+  };
+  for (int nt = 0; nt < n_tiles; ++nt)
+    for (int s = 0; s < out->n_steps; ++s) {
+      uint8_t* dst = img.data() + (static_cast<size_t>(nt) * out->n_steps + s) * out->step_bytes;
+      const StepDesc& sd = steps[s];
+      for (int n = 0; n < out->n_tile; ++n) {
+        const int o = nt * out->n_tile + n;
+        if (out->kind == CONV_STEM) {
+          // image [kchunk j (2)][n][16 B]; 16 B = [dy][dx][c4]; pixel column block b = 2*bp + j
+          for (int j = 0; j < 2; ++j)
+            for (int t = 0; t < 16; ++t) {
+              const int dy = t >> 3, dx = (t >> 2) & 1, c = t & 3;
+              const int kh = 2 * sd.kh + dy - 1, kw = 2 * (2 * sd.kw + j) + dx - 1;
+              int8_t v = 0;
+              if (c < 3 && kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = W(o, c, kh, kw);
+              dst[static_cast<size_t>(j) * out->n_tile * 16 + n * 16 + t] = static_cast<uint8_t>(v);
+            }
+        } else {
+          for (int k = 0; k < out->rowb; ++k)
+            dst[swz_off(n, k, out->rowb)] = static_cast<uint8_t>(W(o, sd.kb * out->rowb + k, sd.kh, sd.kw));
+        }
+      }
+    }
+  DLQ_CUDA(ctx, cudaMalloc(&out->d_img, img.size()));
+  DLQ_CUDA(ctx, cudaMemcpyAsync(out->d_img, img.data(), img.size(), cudaMemcpyHostToDevice, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DLQ_OK;
+}
+
+int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
+              const float* beta, const Act* residual, float res_scale, int relu, float out_scale, int32_t* acc_out,
+              ConvLaunch* L) {
+  ConvKernelParams& p = L->p;
+  memset(&p, 0, sizeof(p));
+  const int rowb = w->rowb;
+  L->rowb = rowb;
+  int es = 1;
+  switch (w->kind) {
+    case CONV_S1:
+      DLQ_ARG(ctx, in.C == w->IC, "input channel mismatch");
+      DLQ_ARG(ctx, in.PR >= w->pH, "input tensor needs PR >= pad");
+      p.Ho = in.H + 2 * w->pH - w->kH + 1;
+      p.Wo = in.W + 2 * w->pW - w->kW + 1;
+      p.Wp = in.W + 2 * w->pW;
+      p.Pv = in.H + in.PR;
+      break;
+    case CONV_S2_3x3:
+    case CONV_S2_1x1:
+      DLQ_ARG(ctx, in.C == w->IC, "input channel mismatch");
+      DLQ_ARG(ctx, in.H % 2 == 0 && in.W % 2 == 0, "stride-2 conv needs even H, W");
+      DLQ_ARG(ctx, in.PR >= 1 && (in.H + in.PR) % 2 == 0, "stride-2 conv needs PR >= 1 and even image pitch");
+      es = 2;
+      p.Ho = in.H / 2;
+      p.Wo = in.W / 2;
+      p.Wp = w->kind == CONV_S2_3x3 ? p.Wo + 1 : p.Wo;
+      p.Pv = (in.H + in.PR) / 2;
+      break;
+    case CONV_STEM:
+      DLQ_ARG(ctx, in.C == 16 && in.PR >= 2, "stem expects the 2x2 space-to-depth input (16 B/pixel, PR >= 2)");
+      p.Ho = in.H + 3 - 4 + 1;
+      p.Wo = in.W + 3 - 4 + 1;
+      p.Wp = in.W + 3;
+      p.Pv = in.H + in.PR;
+      break;
+  }
+  DLQ_ARG(ctx, out.N == in.N && out.H == p.Ho && out.W == p.Wo && out.C == w->OC, "output tensor geometry mismatch");
+  if (residual)
+    DLQ_ARG(ctx, residual->N == in.N && residual->H == p.Ho && residual->W == p.Wo && residual->C == w->OC,
+            "residual tensor geometry mismatch");
+  p.N = in.N;
+  p.OC = w->OC;
+  p.n_tile = w->n_tile;
+  p.row_mul = es;
+
+  std::vector<SubDesc> subs;
+  std::vector<StepDesc> steps;
+  make_schedule(w, subs, steps);
+  p.n_sub = static_cast<int>(subs.size());
+  p.n_steps = static_cast<int>(steps.size());
+  p.k32_per_step = w->kind == CONV_STEM ? 1 : rowb / 32;
+  p.step_bytes = w->step_bytes;
+  p.wimg = w->d_img;
+  int maxshift = 0;
+  for (int k = 0; k < p.n_steps; ++k) {
+    const int sh = steps[k].da * p.Wp + steps[k].db;
+    p.steps[k].a_off = static_cast<uint32_t>(sh) * rowb;
+    maxshift = std::max(maxshift, sh + (w->kind == CONV_STEM ? 1 : 0));
+  }
+  for (int s = 0; s < p.n_sub; ++s) {
+    p.sub_c0[s] = static_cast<int16_t>(subs[s].c0);
+    p.sub_col0[s] = static_cast<int16_t>(subs[s].col0);
+    p.sub_row_off[s] = static_cast<int16_t>(in.PR + subs[s].row_off_rel);
+  }
+  {
+    int k = 0;
+    for (int s = 0; s < p.n_sub; ++s) {
+      p.sub_step0[s] = static_cast<int16_t>(k);
+      while (k < p.n_steps && steps[k].sub == s) ++k;
+    }
+    p.sub_step0[p.n_sub] = static_cast<int16_t>(p.n_steps);
+  }
+
+  // ---- tile shape: MT tiles of 128 positions per super-tile, two TMEM accumulator stages when they fit
+  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 2048 /*alpha,beta,barriers*/;
+  const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
+  int MT = std::max(1, 256 / p.n_tile);
+  int NR = 0;
+  for (;; MT >>= 1) {
+    NR = (p.Wp - 1 + MT * kTileM - 1 + maxshift) / p.Wp + 1;
+    p.tma_bytes = NR * p.Wp * rowb;
+    p.sub_bytes = (p.tma_bytes + 1023) & ~1023;
+    p.b_stages = std::min(p.n_steps, 4);
+    const size_t b_bytes = static_cast<size_t>(p.b_stages) * b_stage_bytes;
+    const int want_a = std::min(4, p.n_sub + 1);
+    const int fit_a = budget > b_bytes ? static_cast<int>((budget - b_bytes) / p.sub_bytes) : 0;
+    p.a_stages = std::min(want_a, fit_a);
+    if ((p.a_stages >= 2 && es * NR <= 256) || MT == 1) break;
+  }
+  DLQ_ARG(ctx, p.a_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256, "conv patch does not fit shared memory / TMA box");
+  p.MT = MT;
+  p.acc_stages = (2 * MT * p.n_tile <= 512) ? 2 : 1;
+  const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
+  p.num_super = static_cast<int>((total_pos + MT * kTileM - 1) / (MT * kTileM));
+
+  // ---- epilogue
+  p.alpha = alpha;
+  p.beta = beta;
+  p.residual = residual ? residual->ptr : nullptr;
+  p.res_PR = residual ? residual->PR : 0;
+  p.res_scale = res_scale;
+  p.relu = relu;
+  p.inv_out_scale = inv_scale(out_scale);
+  p.out = out.ptr;
+  p.out_PR = out.PR;
+  p.acc_out = acc_out;
+
+  // ---- TMA descriptor over the row-padded NHWC input: dims (C bytes, W, rows)
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) {
+    ctx->err = "cuTensorMapEncodeTiled entry point not available";
+    return DLQ_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in.W),
+                        static_cast<cuuint64_t>(in.rows())};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in.C) * in.W};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb), static_cast<cuuint32_t>(es * p.Wp),
+                       static_cast<cuuint32_t>(es * NR)};
+  cuuint32_t estr[3] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es)};
+  const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = enc(&L->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, in.ptr, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ctx->err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+    return DLQ_ERR_CUDA;
+  }
+
+  const int n_tiles = w->OC / w->n_tile;
+  L->grid = dim3(static_cast<unsigned>(std::min(p.num_super, std::max(1, ctx->num_sms / n_tiles))),
+                 static_cast<unsigned>(n_tiles), 1);
+  L->block = dim3(128 + 8 * 32, 1, 1);
+  L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
+            2 * sizeof(float) * p.n_tile + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
+  return DLQ_OK;
+}
+
+template <int ROWB>
+static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
+  static size_t configured[16] = {0};   // per-device max dynamic smem already requested
+  if (configured[ctx->device & 15] < L.smem) {
+    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(ctx->smem_optin)));
+    configured[ctx->device & 15] = ctx->smem_optin;
+  }
+  conv_i8_kernel<ROWB><<<L.grid, L.block, L.smem, ctx->stream>>>(L.tmap, L.p);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+
+int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {
+  switch (L.rowb) {
+    case 16: return launch_t<16>(ctx, L);
+    case 64: return launch_t<64>(ctx, L);
+    case 128: return launch_t<128>(ctx, L);
+  }
+  ctx->err = "internal: bad rowb";
+  return DLQ_ERR_ARG;
+}
+
+}  // namespace dlq

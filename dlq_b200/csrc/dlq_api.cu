@@ -1,0 +1,610 @@
+// dlq_api.cu — C ABI glue: context, per-layer convolution entry point, the ResNet-18 runner
+// (static buffer plan, one launch sequence per batch size) and the batch-sharded multi-GPU driver.
+//
+// Reference anchors: runtime/infer_e2e.cu:102-136 (conv2d_nchw_im2col_gemm), :156-203
+// (basic_block_forward), :206-219 (fc_forward), :254-433 (network wiring, checkpoints).
+#include "dlq_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <thread>
+
+using namespace dlq;
+
+// ================================================================================================
+// context
+// ================================================================================================
+extern "C" {
+
+const char* dlq_version(void) { return "dlq_b200 0.1 (sm_100a)"; }
+
+int dlq_create(int device, dlq_ctx** out) {
+  if (!out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return DLQ_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DLQ_ERR_CUDA;
+  if (prop.major != 10) {
+    fprintf(stderr, "dlq_b200: device %d is sm_%d%d; this library contains sm_100a code only\n", device, prop.major,
+            prop.minor);
+    return DLQ_ERR_CUDA;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return DLQ_ERR_CUDA;
+  dlq_ctx* c = new dlq_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return DLQ_ERR_CUDA;
+  }
+  c->own_stream = true;
+  *out = c;
+  return DLQ_OK;
+}
+
+void dlq_destroy(dlq_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < 4; ++i)
+    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* dlq_last_error_string(const dlq_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dlq_sync(dlq_ctx* ctx) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DLQ_OK;
+}
+void* dlq_stream(dlq_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+int dlq_set_stream(dlq_ctx* ctx, void* stream) {
+  if (!ctx) return DLQ_ERR_ARG;
+  if (ctx->own_stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    ctx->own_stream = false;
+  }
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  return DLQ_OK;
+}
+
+// deterministic synthetic data: SplitMix64 keyed by (seed, FNV-1a(name)); SURVEY §8d
+void dlq_synth_fill_f32(float* v, size_t n, uint64_t seed, const char* name, int lo, int hi, int shift) {
+  uint64_t h = 0xCBF29CE484222325ULL;
+  for (const unsigned char* p = reinterpret_cast<const unsigned char*>(name); *p; ++p) {
+    h ^= *p;
+    h *= 0x100000001B3ULL;
+  }
+  uint64_t s = seed * 0xD1342543DE82EF95ULL + h;
+  auto next = [&s]() {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+  };
+  (void)next();
+  const uint64_t span = static_cast<uint64_t>(hi - lo + 1);
+  const float scale = std::ldexp(1.0f, -shift);
+  for (size_t i = 0; i < n; ++i) v[i] = static_cast<float>(lo + static_cast<int>(next() % span)) * scale;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// weight quantisation helpers (host; QUANT_SPEC §1-§3)
+// ================================================================================================
+namespace {
+
+inline int8_t quant_host(float t, int lo, int hi) {
+  float r = std::nearbyintf(t);   // round-half-to-even under the default rounding mode
+  if (!(r >= static_cast<float>(lo))) r = static_cast<float>(lo);
+  if (r > static_cast<float>(hi)) r = static_cast<float>(hi);
+  return static_cast<int8_t>(static_cast<int>(r));
+}
+
+void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s) {
+  q.resize(static_cast<size_t>(rows) * K);
+  s.resize(rows);
+  for (int r = 0; r < rows; ++r) {
+    float am = 0.f;
+    for (int k = 0; k < K; ++k) am = std::max(am, std::fabs(w[static_cast<size_t>(r) * K + k]));
+    const float sc = am > 0.f ? static_cast<float>(static_cast<double>(am) / 127.0) : 1.0f;
+    s[r] = sc;
+    const float inv = inv_scale(sc);
+    for (int k = 0; k < K; ++k) q[static_cast<size_t>(r) * K + k] = quant_host(w[static_cast<size_t>(r) * K + k] * inv, -127, 127);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// per-layer convolution
+// ================================================================================================
+extern "C" {
+
+int dlq_conv_weights_pack_i8(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                             int pW, dlq_conv_weights** out) {
+  if (!ctx || !out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  DLQ_ARG(ctx, wq != nullptr, "null weights");
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<dlq_conv_weights> w(new dlq_conv_weights());
+  const int rc = pack_conv_weights(ctx, wq, OC, IC, kH, kW, sH, sW, pH, pW, w.get());
+  if (rc != DLQ_OK) {
+    if (w->d_img) cudaFree(w->d_img);
+    return rc;
+  }
+  w->scale.assign(OC, 1.0f);
+  *out = w.release();
+  return DLQ_OK;
+}
+
+int dlq_conv_weights_pack(dlq_ctx* ctx, const float* w_host, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                          int pW, float* w_scale_host, dlq_conv_weights** out) {
+  if (!ctx || !out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  DLQ_ARG(ctx, w_host != nullptr && OC > 0 && IC > 0 && kH > 0 && kW > 0, "null weights or bad dims");
+  std::vector<int8_t> q;
+  std::vector<float> s;
+  quantize_rows(w_host, OC, IC * kH * kW, q, s);
+  const int rc = dlq_conv_weights_pack_i8(ctx, q.data(), OC, IC, kH, kW, sH, sW, pH, pW, out);
+  if (rc != DLQ_OK) return rc;
+  (*out)->scale = s;
+  if (w_scale_host) std::copy(s.begin(), s.end(), w_scale_host);
+  return DLQ_OK;
+}
+
+void dlq_conv_weights_free(dlq_conv_weights* w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  if (w->d_img) cudaFree(w->d_img);
+  delete w;
+}
+
+int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                  const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && w && N >= 0 && C == w->IC && H > 0 && W > 0, "null pointer or dims do not match the packed weights");
+  DLQ_ARG(ctx, (y == nullptr) || (ep != nullptr && ep->alpha && ep->beta && ep->out_scale > 0.f),
+          "an int8 output needs an epilogue with alpha, beta and a positive out_scale");
+  DLQ_ARG(ctx, y || acc_out, "no output requested");
+  int oh, ow;
+  conv_out_dims(w, H, W, &oh, &ow);
+  DLQ_ARG(ctx, oh > 0 && ow > 0, "empty output");
+  if (OH) *OH = oh;
+  if (OW) *OW = ow;
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  Act in, out, res;
+  in.N = N; in.PR = conv_required_in_pr(w);
+  if (w->kind == CONV_STEM) {
+    DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
+    in.H = H / 2; in.W = W / 2; in.C = 16;
+  } else {
+    in.H = H; in.W = W; in.C = C;
+  }
+  out.N = N; out.H = oh; out.W = ow; out.C = w->OC; out.PR = 0;
+  res = out;
+  in.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 0, in.bytes()));
+  DLQ_ARG(ctx, in.ptr != nullptr, "out of device memory (scratch)");
+  DLQ_CUDA(ctx, cudaMemsetAsync(in.ptr, 0, in.bytes(), ctx->stream));
+  int rc = (w->kind == CONV_STEM) ? nchw_i8_to_stem_s2d(ctx, x, N, H, W, in) : nchw_to_act_i8(ctx, x, in);
+  if (rc != DLQ_OK) return rc;
+  if (y) {
+    out.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 1, out.bytes()));
+    DLQ_ARG(ctx, out.ptr != nullptr, "out of device memory (scratch)");
+  }
+  const bool has_res = ep && ep->residual;
+  if (has_res) {
+    res.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 2, res.bytes()));
+    DLQ_ARG(ctx, res.ptr != nullptr, "out of device memory (scratch)");
+    rc = nchw_to_act_i8(ctx, ep->residual, res);
+    if (rc != DLQ_OK) return rc;
+  }
+  int32_t* acc_nhwc = nullptr;
+  if (acc_out) {
+    acc_nhwc = static_cast<int32_t*>(ctx_scratch(ctx, 3, static_cast<size_t>(N) * oh * ow * w->OC * 4));
+    DLQ_ARG(ctx, acc_nhwc != nullptr, "out of device memory (scratch)");
+  }
+  ConvLaunch L;
+  rc = plan_conv(ctx, w, in, out, ep ? ep->alpha : nullptr, ep ? ep->beta : nullptr, has_res ? &res : nullptr,
+                 ep ? ep->res_scale : 0.f, ep ? ep->relu : 0, ep ? ep->out_scale : 1.f, acc_nhwc, &L);
+  if (rc != DLQ_OK) return rc;
+  rc = launch_conv(ctx, L);
+  if (rc != DLQ_OK) return rc;
+  if (y) {
+    rc = act_to_nchw_i8(ctx, out, y);
+    if (rc != DLQ_OK) return rc;
+  }
+  if (acc_out) {
+    rc = nhwc_to_nchw_i32(ctx, acc_nhwc, N, w->OC, oh * ow, acc_out);
+    if (rc != DLQ_OK) return rc;
+  }
+  return DLQ_OK;
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// ResNet-18 runner
+// ================================================================================================
+struct dlq_resnet18 {
+  dlq_ctx* ctx = nullptr;
+  int max_batch = 0;
+  dlq_conv_weights* conv[DLQ_NUM_CONVS] = {nullptr};
+  float* d_alpha[DLQ_NUM_CONVS] = {nullptr};
+  float* d_beta[DLQ_NUM_CONVS] = {nullptr};
+  float act_scale[DLQ_NUM_ACTS];
+  int8_t* d_fc_w = nullptr;
+  float* d_fc_scale = nullptr;
+  float* d_fc_bias = nullptr;
+  int8_t* d_gap_q = nullptr;
+  // activation buffers (row-padded NHWC), geometry for max_batch
+  Act a_in, a_stem, a_pool;
+  Act a_t1[8], a_ds[8], a_out[8];
+  std::vector<void*> allocs;
+  float* d_x = nullptr;       // staging for forward_host
+  float* d_logits = nullptr;
+  struct Plan {
+    int N = 0;
+    ConvLaunch L[DLQ_NUM_CONVS];
+  };
+  std::map<int, std::unique_ptr<Plan>> plans;
+  int last_N = 0;
+};
+
+namespace {
+
+struct BlockCfg { int ic, oc, stride; bool down; };
+const BlockCfg kBlocks[8] = {{64, 64, 1, false},  {64, 64, 1, false},   {64, 128, 2, true},  {128, 128, 1, false},
+                             {128, 256, 2, true}, {256, 256, 1, false}, {256, 512, 2, true}, {512, 512, 1, false}};
+
+Act with_n(const Act& a, int N) {
+  Act b = a;
+  b.N = N;
+  return b;
+}
+
+int alloc_act(dlq_resnet18* m, Act& a, int N, int H, int W, int C, int PR) {
+  a.N = N; a.H = H; a.W = W; a.C = C; a.PR = PR;
+  void* p = nullptr;
+  const size_t bytes = a.bytes() + 1024;
+  DLQ_CUDA(m->ctx, cudaMalloc(&p, bytes));
+  DLQ_CUDA(m->ctx, cudaMemsetAsync(p, 0, bytes, m->ctx->stream));
+  a.ptr = static_cast<int8_t*>(p);
+  m->allocs.push_back(p);
+  return DLQ_OK;
+}
+
+template <typename T>
+int upload(dlq_resnet18* m, const std::vector<T>& h, T** d) {
+  void* p = nullptr;
+  DLQ_CUDA(m->ctx, cudaMalloc(&p, h.size() * sizeof(T)));
+  DLQ_CUDA(m->ctx, cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, m->ctx->stream));
+  DLQ_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+  *d = static_cast<T*>(p);
+  m->allocs.push_back(p);
+  return DLQ_OK;
+}
+
+// activation-scale indices (must match the oracle's enum)
+inline int act_c1(int b) { return 2 + 3 * b; }
+inline int act_ds(int b) { return 3 + 3 * b; }
+inline int act_out(int b) { return 4 + 3 * b; }
+constexpr int kActInput = 0, kActStem = 1, kActGap = 26;
+
+int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
+  dlq_ctx* ctx = m->ctx;
+  P->N = N;
+  const float* S = m->act_scale;
+  int rc = plan_conv(ctx, m->conv[0], with_n(m->a_in, N), with_n(m->a_stem, N), m->d_alpha[0], m->d_beta[0], nullptr, 0.f, 1,
+                     S[kActStem], nullptr, &P->L[0]);
+  if (rc != DLQ_OK) return rc;
+  Act cur = with_n(m->a_pool, N);
+  float s_cur = S[kActStem];
+  for (int b = 0; b < 8; ++b) {
+    const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, id = 3 + 3 * b;
+    Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
+    rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, S[act_c1(b)], nullptr,
+                   &P->L[i1]);
+    if (rc != DLQ_OK) return rc;
+    if (kBlocks[b].down) {
+      Act ds = with_n(m->a_ds[b], N);
+      rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, S[act_ds(b)], nullptr,
+                     &P->L[id]);
+      if (rc != DLQ_OK) return rc;
+      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &ds, S[act_ds(b)], 1, S[act_out(b)], nullptr,
+                     &P->L[i2]);
+    } else {
+      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &cur, s_cur, 1, S[act_out(b)], nullptr,
+                     &P->L[i2]);
+    }
+    if (rc != DLQ_OK) return rc;
+    cur = o;
+    s_cur = S[act_out(b)];
+  }
+  return DLQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void dlq_resnet18_destroy(dlq_resnet18* m) {
+  if (!m) return;
+  cudaSetDevice(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  for (void* p : m->allocs) cudaFree(p);
+  for (auto& c : m->conv) dlq_conv_weights_free(c);
+  delete m;
+}
+
+int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_batch, dlq_resnet18** out) {
+  if (!ctx || !out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  DLQ_ARG(ctx, w && max_batch > 0, "null weights or non-positive batch");
+  for (int i = 0; i < DLQ_NUM_ACTS; ++i) {
+    const bool used = !(i >= 2 && i < 26 && (i - 2) % 3 == 1 && !kBlocks[(i - 2) / 3].down);
+    DLQ_ARG(ctx, !used || (w->act_scale[i] > 0.f && std::isfinite(w->act_scale[i])), "activation scales must be positive");
+  }
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::unique_ptr<dlq_resnet18, void (*)(dlq_resnet18*)> m(new dlq_resnet18(), dlq_resnet18_destroy);
+  m->ctx = ctx;
+  m->max_batch = max_batch;
+  std::copy(w->act_scale, w->act_scale + DLQ_NUM_ACTS, m->act_scale);
+
+  // ---- convs: geometry as wired by runtime/infer_e2e.cu:258-407
+  struct CG { int ic, oc, k, s, p; float s_in; };
+  CG geo[DLQ_NUM_CONVS];
+  geo[0] = {3, 64, 7, 2, 3, w->act_scale[kActInput]};
+  {
+    float s_cur = w->act_scale[kActStem];
+    for (int b = 0; b < 8; ++b) {
+      const BlockCfg& B = kBlocks[b];
+      geo[1 + 3 * b] = {B.ic, B.oc, 3, B.stride, 1, s_cur};
+      geo[2 + 3 * b] = {B.oc, B.oc, 3, 1, 1, w->act_scale[act_c1(b)]};
+      geo[3 + 3 * b] = {B.ic, B.oc, 1, B.stride, 0, s_cur};
+      s_cur = w->act_scale[act_out(b)];
+    }
+  }
+  for (int i = 0; i < DLQ_NUM_CONVS; ++i) {
+    const bool present = (i == 0) || ((i - 1) % 3 != 2) || kBlocks[(i - 1) / 3].down;
+    if (!present) continue;
+    DLQ_ARG(ctx, w->conv_w[i] && w->bn_gamma[i] && w->bn_beta[i] && w->bn_mean[i] && w->bn_var[i], "missing conv/bn weights");
+    const CG& g = geo[i];
+    std::vector<float> s_w(g.oc);
+    int rc = dlq_conv_weights_pack(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i]);
+    if (rc != DLQ_OK) return rc;
+    // folded constants, QUANT_SPEC §3: a = gamma / sqrt(var + eps) in double, rounded once
+    std::vector<float> alpha(g.oc), beta(g.oc);
+    for (int oc = 0; oc < g.oc; ++oc) {
+      const double a = static_cast<double>(w->bn_gamma[i][oc]) / std::sqrt(static_cast<double>(w->bn_var[i][oc]) + static_cast<double>(1e-5f));
+      alpha[oc] = static_cast<float>(static_cast<double>(g.s_in) * static_cast<double>(s_w[oc]) * a);
+      beta[oc] = static_cast<float>(static_cast<double>(w->bn_beta[i][oc]) - static_cast<double>(w->bn_mean[i][oc]) * a);
+    }
+    rc = upload(m.get(), alpha, &m->d_alpha[i]);
+    if (rc != DLQ_OK) return rc;
+    rc = upload(m.get(), beta, &m->d_beta[i]);
+    if (rc != DLQ_OK) return rc;
+  }
+  // ---- FC (R/infer_e2e.cu:206-219): per-row int8, scale folded with the GAP activation scale
+  DLQ_ARG(ctx, w->fc_w && w->fc_b, "missing fc weights");
+  {
+    std::vector<int8_t> q;
+    std::vector<float> s;
+    quantize_rows(w->fc_w, 1000, 512, q, s);
+    std::vector<float> sc(1000), bias(w->fc_b, w->fc_b + 1000);
+    for (int o = 0; o < 1000; ++o) sc[o] = static_cast<float>(static_cast<double>(w->act_scale[kActGap]) * static_cast<double>(s[o]));
+    int rc = upload(m.get(), q, &m->d_fc_w);
+    if (rc != DLQ_OK) return rc;
+    rc = upload(m.get(), sc, &m->d_fc_scale);
+    if (rc != DLQ_OK) return rc;
+    rc = upload(m.get(), bias, &m->d_fc_bias);
+    if (rc != DLQ_OK) return rc;
+  }
+  // ---- activation buffers
+  const int N = max_batch;
+  int rc = alloc_act(m.get(), m->a_in, N, 112, 112, 16, 2);
+  if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_stem, N, 112, 112, 64, 0);
+  if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_pool, N, 56, 56, 64, 1);
+  int hw = 56;
+  for (int b = 0; b < 8 && rc == DLQ_OK; ++b) {
+    const BlockCfg& B = kBlocks[b];
+    if (B.stride == 2) hw /= 2;
+    const bool feeds_s2 = (b + 1 < 8) && kBlocks[b + 1].stride == 2;
+    rc = alloc_act(m.get(), m->a_t1[b], N, hw, hw, B.oc, 1);
+    if (rc == DLQ_OK && B.down) rc = alloc_act(m.get(), m->a_ds[b], N, hw, hw, B.oc, 0);
+    if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_out[b], N, hw, hw, B.oc, feeds_s2 ? 2 : 1);
+  }
+  if (rc != DLQ_OK) return rc;
+  {
+    void* p = nullptr;
+    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 512));
+    m->allocs.push_back(p);
+    m->d_gap_q = static_cast<int8_t*>(p);
+    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 3 * 224 * 224 * sizeof(float)));
+    m->allocs.push_back(p);
+    m->d_x = static_cast<float*>(p);
+    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 1000 * sizeof(float)));
+    m->allocs.push_back(p);
+    m->d_logits = static_cast<float*>(p);
+  }
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // plan the full batch now so the first forward does no host planning
+  std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
+  rc = build_plan(m.get(), N, P.get());
+  if (rc != DLQ_OK) return rc;
+  m->plans[N] = std::move(P);
+  *out = m.release();
+  return DLQ_OK;
+}
+
+int dlq_resnet18_launches(const dlq_resnet18* m) {
+  (void)m;
+  return 1 /*quantise+s2d*/ + 20 /*convs*/ + 1 /*max-pool*/ + 1 /*GAP+FC*/;
+}
+
+int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, x && logits && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  auto it = m->plans.find(N);
+  if (it == m->plans.end()) {
+    std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
+    const int rc = build_plan(m, N, P.get());
+    if (rc != DLQ_OK) return rc;
+    it = m->plans.emplace(N, std::move(P)).first;
+  }
+  const dlq_resnet18::Plan& P = *it->second;
+  const float* S = m->act_scale;
+  int rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N));
+  if (rc != DLQ_OK) return rc;
+  rc = launch_conv(ctx, P.L[0]);
+  if (rc != DLQ_OK) return rc;
+  rc = maxpool_act(ctx, with_n(m->a_stem, N), with_n(m->a_pool, N));
+  if (rc != DLQ_OK) return rc;
+  for (int b = 0; b < 8; ++b) {
+    rc = launch_conv(ctx, P.L[1 + 3 * b]);
+    if (rc != DLQ_OK) return rc;
+    if (kBlocks[b].down) {
+      rc = launch_conv(ctx, P.L[3 + 3 * b]);
+      if (rc != DLQ_OK) return rc;
+    }
+    rc = launch_conv(ctx, P.L[2 + 3 * b]);
+    if (rc != DLQ_OK) return rc;
+  }
+  const Act last = with_n(m->a_out[7], N);
+  const float s_over_hw = static_cast<float>(static_cast<double>(S[act_out(7)]) / static_cast<double>(last.H * last.W));
+  rc = gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
+                  logits);
+  if (rc != DLQ_OK) return rc;
+  m->last_N = N;
+  return DLQ_OK;
+}
+
+int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, x_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_x, x_host, static_cast<size_t>(N) * 3 * 224 * 224 * sizeof(float),
+                                cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = dlq_resnet18_forward(m, m->d_x, N, m->d_logits);
+  if (rc != DLQ_OK) return rc;
+  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, m->d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DLQ_OK;
+}
+
+int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, name && out, "null pointer");
+  DLQ_ARG(ctx, m->last_N > 0, "no forward has run yet");
+  const int N = m->last_N;
+  const std::string s(name);
+  if (s == "gap") {
+    DLQ_CUDA(ctx, cudaMemcpyAsync(out, m->d_gap_q, static_cast<size_t>(N) * 512, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DLQ_OK;
+  }
+  const Act* a = nullptr;
+  if (s == "stem_pool") a = &m->a_pool;
+  else if (s == "stem") a = &m->a_stem;
+  else if (s == "layer1") a = &m->a_out[1];
+  else if (s == "layer2") a = &m->a_out[3];
+  else if (s == "layer3") a = &m->a_out[5];
+  else if (s == "layer4") a = &m->a_out[7];
+  DLQ_ARG(ctx, a != nullptr, "unknown checkpoint name");
+  return act_to_nchw_i8(ctx, with_n(*a, N), out);
+}
+
+}  // extern "C"
+
+// ================================================================================================
+// batch-sharded multi-GPU driver: one context + replica per device, one host thread per device per
+// call, contiguous split, logits gathered straight into the caller's host array (no collective).
+// ================================================================================================
+struct dlq_multi {
+  std::vector<dlq_ctx*> ctx;
+  std::vector<dlq_resnet18*> model;
+  int max_per_dev = 0;
+  std::string err;
+};
+
+extern "C" {
+
+void dlq_multi_destroy(dlq_multi* m) {
+  if (!m) return;
+  for (size_t i = 0; i < m->model.size(); ++i) dlq_resnet18_destroy(m->model[i]);
+  for (size_t i = 0; i < m->ctx.size(); ++i) dlq_destroy(m->ctx[i]);
+  delete m;
+}
+
+int dlq_multi_create(const int* devices, int n_devices, const dlq_resnet18_weights* w, int max_batch_per_device,
+                     dlq_multi** out) {
+  if (!out || !devices || n_devices <= 0 || !w || max_batch_per_device <= 0) return DLQ_ERR_ARG;
+  *out = nullptr;
+  dlq_multi* m = new dlq_multi();
+  m->max_per_dev = max_batch_per_device;
+  for (int i = 0; i < n_devices; ++i) {
+    dlq_ctx* c = nullptr;
+    int rc = dlq_create(devices[i], &c);
+    if (rc != DLQ_OK) {
+      dlq_multi_destroy(m);
+      return rc;
+    }
+    m->ctx.push_back(c);
+    dlq_resnet18* r = nullptr;
+    rc = dlq_resnet18_create(c, w, max_batch_per_device, &r);
+    if (rc != DLQ_OK) {
+      fprintf(stderr, "dlq_multi_create: device %d: %s\n", devices[i], dlq_last_error_string(c));
+      dlq_multi_destroy(m);
+      return rc;
+    }
+    m->model.push_back(r);
+  }
+  *out = m;
+  return DLQ_OK;
+}
+
+const char* dlq_multi_last_error_string(const dlq_multi* m) { return m ? m->err.c_str() : "null"; }
+
+int dlq_multi_forward_host(dlq_multi* m, const float* x_host, int N, float* logits_host) {
+  if (!m || !x_host || !logits_host || N < 0) return DLQ_ERR_ARG;
+  const int G = static_cast<int>(m->ctx.size());
+  const int per = (N + G - 1) / G;
+  if (per > m->max_per_dev) {
+    m->err = "batch exceeds n_devices * max_batch_per_device";
+    return DLQ_ERR_ARG;
+  }
+  std::vector<int> rc(G, DLQ_OK);
+  std::vector<std::thread> th;
+  for (int g = 0; g < G; ++g) {
+    const int n0 = std::min(N, g * per), n1 = std::min(N, (g + 1) * per);
+    if (n1 <= n0) continue;
+    th.emplace_back([=, &rc]() {
+      rc[g] = dlq_resnet18_forward_host(m->model[g], x_host + static_cast<size_t>(n0) * 3 * 224 * 224, n1 - n0,
+                                        logits_host + static_cast<size_t>(n0) * 1000);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int g = 0; g < G; ++g)
+    if (rc[g] != DLQ_OK) {
+      m->err = std::string("device ") + std::to_string(g) + ": " + dlq_last_error_string(m->ctx[g]);
+      return rc[g];
+    }
+  return DLQ_OK;
+}
+
+}  // extern "C"

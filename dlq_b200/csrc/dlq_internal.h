@@ -1,0 +1,109 @@
+// dlq_internal.h — private types shared by the translation units of libdlq_b200.so
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/dlq.h"
+#include "conv_kernel.cuh"
+
+struct dlq_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+  size_t smem_optin = 0;
+  std::string err;
+  // grow-only scratch for the per-layer NCHW entry points (never used by the fused network path)
+  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t scratch_bytes[4] = {0, 0, 0, 0};
+};
+
+#define DLQ_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+      return DLQ_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+#define DLQ_ARG(ctx, cond, msg)                   \
+  do {                                            \
+    if (!(cond)) {                                \
+      (ctx)->err = std::string("bad argument: ") + (msg); \
+      return DLQ_ERR_ARG;                         \
+    }                                             \
+  } while (0)
+
+namespace dlq {
+
+// Row-padded NHWC int8 activation tensor:
+//   rows:  [PR zero rows][image 0: H rows][PR zero rows][image 1: H rows] ...   each row = W*C bytes
+// The zero rows are the vertical conv padding; they are written once (memset) and never again.
+struct Act {
+  int8_t* ptr = nullptr;
+  int N = 0, H = 0, W = 0, C = 0, PR = 0;
+  int rows() const { return PR + N * (H + PR); }
+  size_t bytes() const { return static_cast<size_t>(rows()) * W * C; }
+  size_t row_index(int n, int h) const { return static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR) + h; }
+};
+
+enum ConvKind { CONV_S1 = 0, CONV_S2_3x3 = 1, CONV_S2_1x1 = 2, CONV_STEM = 3 };
+
+}  // namespace dlq
+
+// Packed conv weights: int8 per-output-channel quantised, stored as the exact shared-memory images
+// (swizzle applied) the conv kernel bulk-copies, one image per (n-tile, K step).
+struct dlq_conv_weights {
+  int OC = 0, IC = 0, kH = 0, kW = 0, sH = 1, sW = 1, pH = 0, pW = 0;
+  dlq::ConvKind kind = dlq::CONV_S1;
+  int rowb = 0;        // bytes of K per A row (16 stem / 64 / 128)
+  int kb = 1;          // channel blocks
+  int n_tile = 0;      // output channels per CTA
+  int n_steps = 0;
+  uint32_t step_bytes = 0;
+  uint8_t* d_img = nullptr;   // device: [OC/n_tile][n_steps][step_bytes]
+  std::vector<int8_t> q_oihw; // host copy of the quantised weights (tests / checkpoints)
+  std::vector<float> scale;   // per-output-channel scale
+  int device = 0;
+};
+
+namespace dlq {
+
+// conv_plan.cu
+int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                      int pW, dlq_conv_weights* out);
+// PR the conv requires of its input tensor (and whether the image pitch must be even)
+int conv_required_in_pr(const dlq_conv_weights* w);
+struct ConvLaunch {
+  CUtensorMap tmap;
+  ConvKernelParams p;
+  dim3 grid, block;
+  size_t smem = 0;
+  int rowb = 0;
+};
+// Build the launch for conv `w` reading `in` and writing `out` (either of out.ptr / acc_out may be null).
+int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
+              const float* beta, const Act* residual, float res_scale, int relu, float out_scale, int32_t* acc_out,
+              ConvLaunch* L);
+int launch_conv(dlq_ctx* ctx, const ConvLaunch& L);
+void conv_out_dims(const dlq_conv_weights* w, int H, int W, int* OH, int* OW);
+
+// elementwise.cu (all enqueue on ctx->stream)
+int nchw_to_act_i8(dlq_ctx* ctx, const int8_t* x, const Act& a);          // dense NCHW -> row-padded NHWC
+int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y);                // row-padded NHWC -> dense NCHW
+int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32_t* y);
+int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a);   // C=3 int8 NCHW -> s2d
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a);
+int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out);
+int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
+               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
+
+void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes);
+float inv_scale(float s);
+
+}  // namespace dlq

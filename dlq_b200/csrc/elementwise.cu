@@ -1,0 +1,655 @@
+// elementwise.cu — bandwidth-bound kernels: quantise / dequantise, layout conversion at the NCHW
+// ABI edge, max-pool, global-average-pool + FC, and the standalone BN / ReLU / add operators the
+// reference exposes one kernel each for (cpp/fp32/kernels/{bn_inference,relu,add,maxpool2d,gap_global,
+// softmax}.cu).  All use 128-bit vectorised global accesses and warp-shuffle reductions; grids are
+// sized in multiples of the SM count with grid-stride loops.
+#include "dlq_internal.h"
+#include <algorithm>
+
+namespace dlq {
+
+float inv_scale(float s) { return static_cast<float>(1.0 / static_cast<double>(s)); }
+
+void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes) {
+  if (ctx->scratch_bytes[slot] < bytes) {
+    if (ctx->scratch[slot]) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->scratch[slot]);
+    }
+    ctx->scratch[slot] = nullptr;
+    ctx->scratch_bytes[slot] = 0;
+    if (cudaMalloc(&ctx->scratch[slot], bytes) != cudaSuccess) return nullptr;
+    ctx->scratch_bytes[slot] = bytes;
+  }
+  return ctx->scratch[slot];
+}
+
+static inline int grid_for(dlq_ctx* ctx, size_t work_items, int threads, int max_waves = 8) {
+  const size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(ctx->num_sms) * max_waves;
+  return static_cast<int>(std::max<size_t>(1, std::min(blocks, cap)));
+}
+
+__device__ __forceinline__ int quant_rn(float t, int lo, int hi) {
+  int q = __float2int_rn(t);
+  return max(lo, min(hi, q));
+}
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+  return (static_cast<uint32_t>(a) & 0xFFu) | ((static_cast<uint32_t>(b) & 0xFFu) << 8) |
+         ((static_cast<uint32_t>(c) & 0xFFu) << 16) | ((static_cast<uint32_t>(d) & 0xFFu) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantise / dequantise (flat)
+// ------------------------------------------------------------------------------------------------
+__global__ void quantize_f32_i8_kernel(const float* __restrict__ x, size_t n, float inv_s, int8_t* __restrict__ q) {
+  const size_t n16 = n / 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const float4* src = reinterpret_cast<const float4*>(x) + i * 4;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = __ldg(src + j);
+      w[j] = pack4(quant_rn(__fmul_rn(v.x, inv_s), -128, 127), quant_rn(__fmul_rn(v.y, inv_s), -128, 127),
+                   quant_rn(__fmul_rn(v.z, inv_s), -128, 127), quant_rn(__fmul_rn(v.w, inv_s), -128, 127));
+    }
+    reinterpret_cast<int4*>(q)[i] = make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+  }
+  for (size_t i = n16 * 16 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    q[i] = static_cast<int8_t>(quant_rn(__fmul_rn(x[i], inv_s), -128, 127));
+}
+
+__global__ void dequantize_i8_f32_kernel(const int8_t* __restrict__ q, size_t n, float s, float* __restrict__ x) {
+  const size_t n16 = n / 16;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(q) + i);
+    const int8_t* b = reinterpret_cast<const int8_t*>(&v);
+    float4* dst = reinterpret_cast<float4*>(x) + i * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      dst[j] = make_float4(__fmul_rn((float)b[4 * j], s), __fmul_rn((float)b[4 * j + 1], s),
+                           __fmul_rn((float)b[4 * j + 2], s), __fmul_rn((float)b[4 * j + 3], s));
+  }
+  for (size_t i = n16 * 16 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] = __fmul_rn((float)q[i], s);
+}
+
+__global__ void dequantize_pc_kernel(const int8_t* __restrict__ q, size_t n, int C, int HW,
+                                     const float* __restrict__ s, float* __restrict__ x) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] = __fmul_rn((float)q[i], __ldg(s + (i / HW) % C));
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout conversion: dense NCHW int8  <->  row-padded NHWC int8 (smem-tiled transpose, 32 pixels x 32 ch... )
+// tile: 64 channels x 64 pixels per block iteration; reads coalesced along pixels, writes along channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_act_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ a, int N, int C, int H, int W,
+                                   int PR) {
+  __shared__ int8_t tile[64][64 + 4];
+  const int HW = H * W;
+  const int ptiles = (HW + 63) / 64, ctiles = C / 64;
+  const long long total = static_cast<long long>(N) * ptiles * ctiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = static_cast<int>(t % ctiles);
+    const int pt = static_cast<int>((t / ctiles) % ptiles);
+    const int n = static_cast<int>(t / (static_cast<long long>(ctiles) * ptiles));
+    const int p0 = pt * 64, c0 = ct * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int c = i / 64, pp = i % 64;
+      int8_t v = 0;
+      if (p0 + pp < HW) v = x[(static_cast<size_t>(n) * C + c0 + c) * HW + p0 + pp];
+      tile[c][pp] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int pp = i / 64, c = i % 64;
+      const int pix = p0 + pp;
+      if (pix < HW) {
+        const int h = pix / W, w = pix % W;
+        const size_t row = static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR) + h;
+        a[(row * W + w) * C + c0 + c] = tile[c][pp];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void act_to_nchw_kernel(const int8_t* __restrict__ a, int8_t* __restrict__ y, int N, int C, int H, int W,
+                                   int PR) {
+  __shared__ int8_t tile[64][64 + 4];
+  const int HW = H * W;
+  const int ptiles = (HW + 63) / 64, ctiles = C / 64;
+  const long long total = static_cast<long long>(N) * ptiles * ctiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = static_cast<int>(t % ctiles);
+    const int pt = static_cast<int>((t / ctiles) % ptiles);
+    const int n = static_cast<int>(t / (static_cast<long long>(ctiles) * ptiles));
+    const int p0 = pt * 64, c0 = ct * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int pp = i / 64, c = i % 64;
+      const int pix = p0 + pp;
+      int8_t v = 0;
+      if (pix < HW) {
+        const int h = pix / W, w = pix % W;
+        const size_t row = static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR) + h;
+        v = a[(row * W + w) * C + c0 + c];
+      }
+      tile[c][pp] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+      const int c = i / 64, pp = i % 64;
+      if (p0 + pp < HW) y[(static_cast<size_t>(n) * C + c0 + c) * HW + p0 + pp] = tile[c][pp];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void nhwc_to_nchw_i32_kernel(const int32_t* __restrict__ x, int32_t* __restrict__ y, int N, int C, int HW) {
+  __shared__ int32_t tile[32][33];
+  const int ptiles = (HW + 31) / 32, ctiles = (C + 31) / 32;
+  const long long total = static_cast<long long>(N) * ptiles * ctiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = static_cast<int>(t % ctiles);
+    const int pt = static_cast<int>((t / ctiles) % ptiles);
+    const int n = static_cast<int>(t / (static_cast<long long>(ctiles) * ptiles));
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int pp = i / 32, c = i % 32;
+      int32_t v = 0;
+      if (pt * 32 + pp < HW && ct * 32 + c < C) v = x[(static_cast<size_t>(n) * HW + pt * 32 + pp) * C + ct * 32 + c];
+      tile[pp][c] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) {
+      const int c = i / 32, pp = i % 32;
+      if (pt * 32 + pp < HW && ct * 32 + c < C)
+        y[(static_cast<size_t>(n) * C + ct * 32 + c) * HW + pt * 32 + pp] = tile[pp][c];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem input: [N,3,H,W] -> 2x2 space-to-depth, 16 B per s2d pixel = [dy][dx][c0,c1,c2,0], PR zero rows
+// One thread per s2d pixel: 6 float2 (or 6 char2) loads, one 16-byte store.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool QUANT>
+__global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
+                                float inv_s) {
+  const int H2 = H / 2, W2 = W / 2;
+  const size_t total = static_cast<size_t>(N) * H2 * W2;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int w2 = static_cast<int>(i % W2);
+    const int h2 = static_cast<int>((i / W2) % H2);
+    const int n = static_cast<int>(i / (static_cast<size_t>(W2) * H2));
+    int q[2][2][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const T* src = x + ((static_cast<size_t>(n) * 3 + c) * H + (2 * h2 + dy)) * W + 2 * w2;
+        if constexpr (QUANT) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+          q[dy][0][c] = quant_rn(__fmul_rn(v.x, inv_s), -128, 127);
+          q[dy][1][c] = quant_rn(__fmul_rn(v.y, inv_s), -128, 127);
+        } else {
+          q[dy][0][c] = src[0];
+          q[dy][1][c] = src[1];
+        }
+      }
+    const size_t row = static_cast<size_t>(PR) + static_cast<size_t>(n) * (H2 + PR) + h2;
+    int4 o;
+    o.x = (int)pack4(q[0][0][0], q[0][0][1], q[0][0][2], 0);
+    o.y = (int)pack4(q[0][1][0], q[0][1][1], q[0][1][2], 0);
+    o.z = (int)pack4(q[1][0][0], q[1][0][1], q[1][0][2], 0);
+    o.w = (int)pack4(q[1][1][0], q[1][1][1], q[1][1][2], 0);
+    reinterpret_cast<int4*>(a)[row * W2 + w2] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max-pool 3x3 / s2 / p1 on row-padded NHWC int8; one thread = 16 channels of one output pixel.
+// (geometry of K/maxpool2d.cu:14-40; OOB taps skipped, int8 max is exact after quantisation)
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_act_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int N, int H, int W,
+                                   int C, int PRi, int OH, int OW, int PRo) {
+  const int cv = C / 16;
+  const size_t total = static_cast<size_t>(N) * OH * OW * cv;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c16 = static_cast<int>(i % cv);
+    const int ow = static_cast<int>((i / cv) % OW);
+    const int oh = static_cast<int>((i / (static_cast<size_t>(cv) * OW)) % OH);
+    const int n = static_cast<int>(i / (static_cast<size_t>(cv) * OW * OH));
+    uint32_t m[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+      const size_t row = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + ih;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in + (row * W + iw) * C) + c16);
+        m[0] = __vmaxs4(m[0], (uint32_t)v.x);
+        m[1] = __vmaxs4(m[1], (uint32_t)v.y);
+        m[2] = __vmaxs4(m[2], (uint32_t)v.z);
+        m[3] = __vmaxs4(m[3], (uint32_t)v.w);
+      }
+    }
+    const size_t orow = static_cast<size_t>(PRo) + static_cast<size_t>(n) * (OH + PRo) + oh;
+    reinterpret_cast<int4*>(out + (orow * OW + ow) * C)[c16] = make_int4((int)m[0], (int)m[1], (int)m[2], (int)m[3]);
+  }
+}
+
+// max-pool on dense NCHW int8 (per-layer ABI entry)
+__global__ void maxpool_nchw_i8_kernel(const int8_t* __restrict__ x, int8_t* __restrict__ y, int NC, int H, int W,
+                                       int OH, int OW) {
+  const size_t total = static_cast<size_t>(NC) * OH * OW;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int ow = static_cast<int>(i % OW);
+    const int oh = static_cast<int>((i / OW) % OH);
+    const size_t nc = i / (static_cast<size_t>(OW) * OH);
+    const int8_t* xp = x + nc * H * W;
+    int m = -128;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        m = max(m, (int)xp[ih * W + iw]);
+      }
+    }
+    y[i] = static_cast<int8_t>(m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GAP + FC fused (network tail).  One CTA handles IMG images: phase 1 sums the HxW pixels of each
+// channel (int32, exact), scales and requantises to int8 in smem; phase 2 streams the int8 FC weights
+// once per CTA, each warp producing one output row for all IMG images with dp4a + warp shuffles.
+// (semantics: K/gap_global.cu:10-32 mean, R/infer_e2e.cu:206-219 FC + bias; arithmetic QUANT_SPEC §5)
+// ------------------------------------------------------------------------------------------------
+constexpr int kGapImgs = 8;
+__global__ void __launch_bounds__(512)
+gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
+              float inv_gap_scale, const int8_t* __restrict__ fc_w, const float* __restrict__ fc_scale,
+              const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits) {
+  extern __shared__ int8_t sg[];   // [kGapImgs][C]
+  const int n0 = blockIdx.x * kGapImgs;
+  const int nimg = min(kGapImgs, N - n0);
+  const int HW = H * W;
+  for (int i = threadIdx.x; i < nimg * (C / 4); i += blockDim.x) {
+    const int im = i / (C / 4), c4 = i % (C / 4);
+    const size_t row0 = static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR);
+    const int8_t* src = in + row0 * W * C + c4 * 4;
+    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int px = 0; px < HW; ++px) {
+      const char4 v = *reinterpret_cast<const char4*>(src + static_cast<size_t>(px) * C);
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+    const int q0 = quant_rn(__fmul_rn(__fmul_rn((float)s0, scale_over_hw), inv_gap_scale), -128, 127);
+    const int q1 = quant_rn(__fmul_rn(__fmul_rn((float)s1, scale_over_hw), inv_gap_scale), -128, 127);
+    const int q2 = quant_rn(__fmul_rn(__fmul_rn((float)s2, scale_over_hw), inv_gap_scale), -128, 127);
+    const int q3 = quant_rn(__fmul_rn(__fmul_rn((float)s3, scale_over_hw), inv_gap_scale), -128, 127);
+    const uint32_t pk = pack4(q0, q1, q2, q3);
+    reinterpret_cast<uint32_t*>(sg + im * C)[c4] = pk;
+    if (gap_q) reinterpret_cast<uint32_t*>(gap_q + static_cast<size_t>(n0 + im) * C)[c4] = pk;
+  }
+  __syncthreads();
+  if (!logits) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int o = warp; o < O; o += nwarps) {
+    int acc[kGapImgs];
+#pragma unroll
+    for (int im = 0; im < kGapImgs; ++im) acc[im] = 0;
+    for (int k = lane * 16; k < C; k += 32 * 16) {
+      const int4 wv = __ldg(reinterpret_cast<const int4*>(fc_w + static_cast<size_t>(o) * C + k));
+#pragma unroll
+      for (int im = 0; im < kGapImgs; ++im) {
+        if (im < nimg) {
+          const int4 gv = *reinterpret_cast<const int4*>(sg + im * C + k);
+          acc[im] = __dp4a(wv.x, gv.x, acc[im]);
+          acc[im] = __dp4a(wv.y, gv.y, acc[im]);
+          acc[im] = __dp4a(wv.z, gv.z, acc[im]);
+          acc[im] = __dp4a(wv.w, gv.w, acc[im]);
+        }
+      }
+    }
+#pragma unroll
+    for (int im = 0; im < kGapImgs; ++im) {
+      int a = acc[im];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0 && im < nimg)
+        logits[static_cast<size_t>(n0 + im) * O + o] = __fmaf_rn((float)a, __ldg(fc_scale + o), __ldg(fc_bias + o));
+    }
+  }
+}
+
+// standalone GAP on dense NCHW int8: one warp per (n,c)
+__global__ void gap_nchw_i8_kernel(const int8_t* __restrict__ x, int NC, int HW, float scale_over_hw, float inv_out,
+                                   float* __restrict__ yf, int8_t* __restrict__ yq) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int nc = blockIdx.x * wpb + (threadIdx.x >> 5); nc < NC; nc += gridDim.x * wpb) {
+    int s = 0;
+    for (int i = lane; i < HW; i += 32) s += x[static_cast<size_t>(nc) * HW + i];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) {
+      const float g = __fmul_rn((float)s, scale_over_hw);
+      if (yf) yf[nc] = g;
+      if (yq) yq[nc] = static_cast<int8_t>(quant_rn(__fmul_rn(g, inv_out), -128, 127));
+    }
+  }
+}
+
+// standalone FC: one warp per (n, o)
+__global__ void fc_i8_kernel(const int8_t* __restrict__ g, const int8_t* __restrict__ w, const float* __restrict__ sc,
+                             const float* __restrict__ bias, int N, int O, int I, float* __restrict__ logits) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const long long total = static_cast<long long>(N) * O;
+  for (long long t = static_cast<long long>(blockIdx.x) * wpb + (threadIdx.x >> 5); t < total;
+       t += static_cast<long long>(gridDim.x) * wpb) {
+    const int n = static_cast<int>(t / O), o = static_cast<int>(t % O);
+    int acc = 0;
+    if ((I & 15) == 0) {
+      for (int k = lane * 16; k < I; k += 512) {
+        const int4 wv = __ldg(reinterpret_cast<const int4*>(w + static_cast<size_t>(o) * I + k));
+        const int4 gv = __ldg(reinterpret_cast<const int4*>(g + static_cast<size_t>(n) * I + k));
+        acc = __dp4a(wv.x, gv.x, acc);
+        acc = __dp4a(wv.y, gv.y, acc);
+        acc = __dp4a(wv.z, gv.z, acc);
+        acc = __dp4a(wv.w, gv.w, acc);
+      }
+    } else {
+      for (int k = lane; k < I; k += 32) acc += (int)w[static_cast<size_t>(o) * I + k] * (int)g[static_cast<size_t>(n) * I + k];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) logits[t] = __fmaf_rn((float)acc, __ldg(sc + o), __ldg(bias + o));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone FP32 / int8 element-wise operators (reference surface)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_inference_f32_kernel(float* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                                        const float* __restrict__ m, const float* __restrict__ v, float eps, size_t total,
+                                        int C, int HW) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = static_cast<int>((i / HW) % C);
+    const float y = __fdiv_rn(__fsub_rn(x[i], __ldg(m + c)), __fsqrt_rn(__fadd_rn(__ldg(v + c), eps)));
+    x[i] = __fmaf_rn(__ldg(g + c), y, __ldg(b + c));
+  }
+}
+__global__ void relu_f32_kernel(float* __restrict__ x, size_t n) {
+  const size_t n4 = n / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    if (v.x < 0.f) v.x = 0.f;
+    if (v.y < 0.f) v.y = 0.f;
+    if (v.z < 0.f) v.z = 0.f;
+    if (v.w < 0.f) v.w = 0.f;
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (x[i] < 0.f) x[i] = 0.f;
+}
+__global__ void relu_i8_kernel(int8_t* __restrict__ x, size_t n) {
+  const size_t n16 = n / 16, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    int4 v = reinterpret_cast<int4*>(x)[i];
+    v.x = (int)__vmaxs4((uint32_t)v.x, 0u);
+    v.y = (int)__vmaxs4((uint32_t)v.y, 0u);
+    v.z = (int)__vmaxs4((uint32_t)v.z, 0u);
+    v.w = (int)__vmaxs4((uint32_t)v.w, 0u);
+    reinterpret_cast<int4*>(x)[i] = v;
+  }
+  for (size_t i = n16 * 16 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    if (x[i] < 0) x[i] = 0;
+}
+__global__ void add_f32_kernel(float* __restrict__ y, const float* __restrict__ x, size_t n) {
+  const size_t n4 = n / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = reinterpret_cast<float4*>(y)[i];
+    const float4 b = __ldg(reinterpret_cast<const float4*>(x) + i);
+    a.x = __fadd_rn(a.x, b.x);
+    a.y = __fadd_rn(a.y, b.y);
+    a.z = __fadd_rn(a.z, b.z);
+    a.w = __fadd_rn(a.w, b.w);
+    reinterpret_cast<float4*>(y)[i] = a;
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    y[i] = __fadd_rn(y[i], x[i]);
+}
+// y = quant( relu( y*sy + x*sx ) / so )  — QUANT_SPEC §4: t = (float)y*sy ; t = fmaf((float)x, sx, t)
+__global__ void add_requant_i8_kernel(int8_t* __restrict__ y, float sy, const int8_t* __restrict__ x, float sx, size_t n,
+                                      int relu, float inv_so) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int lo = relu ? 0 : -128;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float t = __fmul_rn((float)y[i], sy);
+    t = __fmaf_rn((float)x[i], sx, t);
+    if (relu && t < 0.f) t = 0.f;
+    y[i] = static_cast<int8_t>(quant_rn(__fmul_rn(t, inv_so), lo, 127));
+  }
+}
+__global__ void softmax_f32_kernel(const float* __restrict__ x, int K, float* __restrict__ y) {
+  __shared__ float red[32];
+  const float* xr = x + static_cast<size_t>(blockIdx.x) * K;
+  float* yr = y + static_cast<size_t>(blockIdx.x) * K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) m = fmaxf(m, xr[i]);
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s += expf(xr[i] - m);
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) yr[i] = expf(xr[i] - m) / s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host wrappers
+// ------------------------------------------------------------------------------------------------
+int nchw_to_act_i8(dlq_ctx* ctx, const int8_t* x, const Act& a) {
+  DLQ_ARG(ctx, a.C % 64 == 0, "channels must be a multiple of 64");
+  const long long tiles = static_cast<long long>(a.N) * ((a.H * a.W + 63) / 64) * (a.C / 64);
+  const int grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms * 16LL));
+  nchw_to_act_kernel<<<std::max(1, grid), 256, 0, ctx->stream>>>(x, a.ptr, a.N, a.C, a.H, a.W, a.PR);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y) {
+  DLQ_ARG(ctx, a.C % 64 == 0, "channels must be a multiple of 64");
+  const long long tiles = static_cast<long long>(a.N) * ((a.H * a.W + 63) / 64) * (a.C / 64);
+  const int grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms * 16LL));
+  act_to_nchw_kernel<<<std::max(1, grid), 256, 0, ctx->stream>>>(a.ptr, y, a.N, a.C, a.H, a.W, a.PR);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32_t* y) {
+  const long long tiles = static_cast<long long>(N) * ((HW + 31) / 32) * ((C + 31) / 32);
+  const int grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms * 16LL));
+  nhwc_to_nchw_i32_kernel<<<std::max(1, grid), 256, 0, ctx->stream>>>(x, y, N, C, HW);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a) {
+  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 && a.C == 16, "stem s2d geometry");
+  const size_t total = static_cast<size_t>(N) * a.H * a.W;
+  stem_s2d_kernel<int8_t, false><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a) {
+  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 && a.C == 16, "stem s2d geometry");
+  const size_t total = static_cast<size_t>(N) * a.H * a.W;
+  stem_s2d_kernel<float, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
+  DLQ_ARG(ctx, in.C % 16 == 0 && out.C == in.C && out.N == in.N, "maxpool geometry");
+  const size_t total = static_cast<size_t>(in.N) * out.H * out.W * (in.C / 16);
+  maxpool_act_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR,
+                                                                         out.H, out.W, out.PR);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
+               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits) {
+  DLQ_ARG(ctx, in.C % 512 == 0 || in.C % 16 == 0, "gap channels");
+  DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
+  const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
+  gap_fc_kernel<<<blocks, 512, kGapImgs * in.C, ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
+                                                               inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+
+}  // namespace dlq
+
+// ================================================================================================
+// C ABI: element-wise entry points
+// ================================================================================================
+using namespace dlq;
+
+extern "C" {
+
+int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int8_t* q) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && q && scale > 0.f, "null pointer or non-positive scale");
+  if (n == 0) return DLQ_OK;
+  DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+          "pointers must be 16-byte aligned");
+  quantize_f32_i8_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(x, n, inv_scale(scale), q);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_dequantize_i8_f32(dlq_ctx* ctx, const int8_t* q, size_t n, float scale, float* x) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && q, "null pointer");
+  if (n == 0) return DLQ_OK;
+  DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
+          "pointers must be 16-byte aligned");
+  dequantize_i8_f32_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(q, n, scale, x);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_dequantize_i8_f32_per_channel(dlq_ctx* ctx, const int8_t* q, int N, int C, int HW, const float* scale,
+                                      float* x) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && q && scale && N >= 0 && C > 0 && HW > 0, "null pointer or bad dims");
+  const size_t n = static_cast<size_t>(N) * C * HW;
+  if (n == 0) return DLQ_OK;
+  dequantize_pc_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(q, n, C, HW, scale, x);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_bn_inference_f32(dlq_ctx* ctx, float* x, const float* g, const float* b, const float* m, const float* v,
+                         float eps, int N, int C, int OH, int OW) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && g && b && m && v && C > 0 && OH > 0 && OW > 0 && N >= 0, "null pointer or bad dims");
+  const size_t total = static_cast<size_t>(N) * C * OH * OW;
+  if (total == 0) return DLQ_OK;
+  bn_inference_f32_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, g, b, m, v, eps, total, C, OH * OW);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_relu_forward_f32(dlq_ctx* ctx, float* x, size_t n) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x || n == 0, "null pointer");
+  if (n == 0) return DLQ_OK;
+  relu_f32_kernel<<<grid_for(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(x, n);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_relu_forward_i8(dlq_ctx* ctx, int8_t* x, size_t n) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x || n == 0, "null pointer");
+  if (n == 0) return DLQ_OK;
+  relu_i8_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(x, n);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_add_inplace_f32(dlq_ctx* ctx, float* y, const float* x, size_t n) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, (x && y) || n == 0, "null pointer");
+  if (n == 0) return DLQ_OK;
+  add_f32_kernel<<<grid_for(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(y, x, n);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_add_requant_i8(dlq_ctx* ctx, int8_t* y, float y_scale, const int8_t* x, float x_scale, size_t n, int relu,
+                       float out_scale) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, ((x && y) || n == 0) && out_scale > 0.f, "null pointer or non-positive scale");
+  if (n == 0) return DLQ_OK;
+  add_requant_i8_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(y, y_scale, x, x_scale, n, relu,
+                                                                        inv_scale(out_scale));
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_maxpool2d_3x3_s2p1_nchw_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, int8_t* y) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && y && N >= 0 && C > 0 && H > 0 && W > 0, "null pointer or bad dims");
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const size_t total = static_cast<size_t>(N) * C * OH * OW;
+  if (total == 0) return DLQ_OK;
+  maxpool_nchw_i8_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, y, N * C, H, W, OH, OW);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_gap_global_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, float in_scale, float out_scale,
+                      float* y_f32, int8_t* y_i8) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && N >= 0 && C > 0 && H > 0 && W > 0 && (y_f32 || y_i8), "null pointer or bad dims");
+  DLQ_ARG(ctx, !y_i8 || out_scale > 0.f, "non-positive output scale");
+  if (N == 0) return DLQ_OK;
+  const float s_over_hw = static_cast<float>(static_cast<double>(in_scale) / static_cast<double>(H * W));
+  gap_nchw_i8_kernel<<<grid_for(ctx, static_cast<size_t>(N) * C * 32, 256), 256, 0, ctx->stream>>>(
+      x, N * C, H * W, s_over_hw, y_i8 ? inv_scale(out_scale) : 0.f, y_f32, y_i8);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_fc_forward_i8(dlq_ctx* ctx, const int8_t* g, const int8_t* w, const float* scale, const float* bias, int N,
+                      int O, int I, float* logits) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, g && w && scale && bias && logits && N >= 0 && O > 0 && I > 0, "null pointer or bad dims");
+  if (N == 0) return DLQ_OK;
+  fc_i8_kernel<<<grid_for(ctx, static_cast<size_t>(N) * O * 32, 256), 256, 0, ctx->stream>>>(g, w, scale, bias, N, O, I,
+                                                                                            logits);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_softmax_f32(dlq_ctx* ctx, const float* x, int N, int K, float* y) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && y && N >= 0 && K > 0, "null pointer or bad dims");
+  if (N == 0) return DLQ_OK;
+  softmax_f32_kernel<<<N, 256, 0, ctx->stream>>>(x, K, y);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+/* dlq.h — C ABI of libdlq_b200.so: B200-native INT8 inference operators for the DLQ lab's ResNet-18
+ * kernel stack.
+ *
+ * The reference (yeontachi/DLQ, CUDA/resnet18-kernel-lab) has no FFI layer: its boundary is a set of
+ * `extern "C" __global__` FP32 kernels launched directly from host code plus a few host launcher
+ * helpers.  Each entry point below is the host-callable replacement for one of those, with the same
+ * argument order and meaning (device pointers, dense NCHW, dims as int), cited as
+ *   K/ = CUDA/resnet18-kernel-lab/cpp/fp32/kernels/      R/ = .../cpp/fp32/runtime/
+ *
+ * Conventions
+ *   - every function returns int: 0 ok, 1 bad argument, 3 CUDA launch/runtime error
+ *     (the reference's exit codes, R/utils.hpp:34-45; 2 stays reserved for parity failures in tests);
+ *     dlq_last_error_string() gives the text.  Nothing here ever calls exit().
+ *   - all tensor pointers are DEVICE pointers unless the name says host; the caller owns every buffer.
+ *   - calls enqueue work on the context's stream and return without synchronising.
+ *   - one context per device; a context is not thread-safe, different contexts are independent.
+ *   - quantisation arithmetic is defined by spec/QUANT_SPEC.md (the reference defines none).
+ */
+#ifndef DLQ_H
+#define DLQ_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLQ_OK 0
+#define DLQ_ERR_ARG 1
+#define DLQ_ERR_CUDA 3
+
+typedef struct dlq_ctx dlq_ctx;
+typedef struct dlq_conv_weights dlq_conv_weights;
+typedef struct dlq_resnet18 dlq_resnet18;
+
+/* ------------------------------------------------------------------ context (replaces the reference's
+ * implicit default-stream / cudaMalloc-per-call runtime, R/utils.hpp:122-160) */
+int dlq_create(int device, dlq_ctx** out);
+void dlq_destroy(dlq_ctx* ctx);
+const char* dlq_last_error_string(const dlq_ctx* ctx);
+int dlq_sync(dlq_ctx* ctx);
+void* dlq_stream(dlq_ctx* ctx);                 /* the cudaStream_t work is enqueued on */
+int dlq_set_stream(dlq_ctx* ctx, void* stream); /* adopt a caller-owned cudaStream_t */
+const char* dlq_version(void);
+
+/* ------------------------------------------------------------------ quantise / dequantise helpers
+ * (absent from the reference — SURVEY §8 a13; arithmetic per QUANT_SPEC §2) */
+/* q = clamp(rne(x * fp32(1/scale)), -128, 127) */
+int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int8_t* q);
+int dlq_dequantize_i8_f32(dlq_ctx* ctx, const int8_t* q, size_t n, float scale, float* x);
+/* x[n,c,hw] = q * scale[c] */
+int dlq_dequantize_i8_f32_per_channel(dlq_ctx* ctx, const int8_t* q, int N, int C, int HW, const float* scale,
+                                      float* x);
+
+/* ------------------------------------------------------------------ convolution
+ * replaces conv2d_nchw_im2col_gemm (R/infer_e2e.cu:102-136) = im2col_nchw (K/im2col.cu:6-58) +
+ * sgemm_tiled (K/sgemm_tiled.cu:6-46), with bn_inference / add_inplace / relu_forward folded into the
+ * epilogue (K/bn_inference.cu:6-28, K/add.cu:3-8, K/relu.cu:5-10). */
+
+/* Pack OIHW fp32 weights (HOST pointer; the reference passes std::vector<float>, R/infer_e2e.cu:105) once:
+ * per-output-channel symmetric int8 (QUANT_SPEC §1) in the kernel's shared-memory image order.
+ * The per-channel scales are returned through w_scale_host[OC] (HOST, may be NULL). */
+int dlq_conv_weights_pack(dlq_ctx* ctx, const float* w_oihw_host, int OC, int IC, int kH, int kW, int sH, int sW,
+                          int pH, int pW, float* w_scale_host, dlq_conv_weights** out);
+/* same from already-quantised int8 OIHW weights (HOST) */
+int dlq_conv_weights_pack_i8(dlq_ctx* ctx, const int8_t* wq_oihw_host, int OC, int IC, int kH, int kW, int sH,
+                             int sW, int pH, int pW, dlq_conv_weights** out);
+void dlq_conv_weights_free(dlq_conv_weights* w);
+
+/* Fused epilogue, QUANT_SPEC §3 (each line one binary32 rounding):
+ *   t = fmaf((float)acc, alpha[oc], beta[oc]);  if (residual) t = fmaf((float)r, res_scale, t);
+ *   if (relu && t < 0) t = 0;  t *= fp32(1/out_scale);  y = clamp(rne(t), relu ? 0 : -128, 127)   */
+typedef struct {
+  const float* alpha;     /* [OC] device */
+  const float* beta;      /* [OC] device */
+  const int8_t* residual; /* NCHW int8 [N,OC,OH,OW] device, or NULL */
+  float res_scale;
+  int relu;
+  float out_scale;
+} dlq_epilogue;
+
+/* x: int8 NCHW [N,C,H,W]; y: int8 NCHW [N,OC,OH,OW] (may be NULL); acc_out: int32 NCHW raw accumulators
+ * (may be NULL; parity/debug).  OH/OW are returned like the reference's int& OH, int& OW. */
+int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                  const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW);
+
+/* ------------------------------------------------------------------ element-wise / pooling (standalone,
+ * kept for per-layer API parity; the fused network path does not launch them) */
+/* K/bn_inference.cu:6-28 — in place, y = g*((x-m)/sqrtf(v+eps)) + b, c = (idx/(OH*OW)) % C */
+int dlq_bn_inference_f32(dlq_ctx* ctx, float* x, const float* g, const float* b, const float* m, const float* v,
+                         float eps, int N, int C, int OH, int OW);
+/* K/relu.cu:5-10 — in place, if (x < 0) x = 0 */
+int dlq_relu_forward_f32(dlq_ctx* ctx, float* x, size_t n);
+int dlq_relu_forward_i8(dlq_ctx* ctx, int8_t* x, size_t n);
+/* K/add.cu:3-8 — y += x */
+int dlq_add_inplace_f32(dlq_ctx* ctx, float* y, const float* x, size_t n);
+/* residual add of two int8 tensors with different scales, requantised: QUANT_SPEC §4 */
+int dlq_add_requant_i8(dlq_ctx* ctx, int8_t* y, float y_scale, const int8_t* x, float x_scale, size_t n, int relu,
+                       float out_scale);
+/* K/maxpool2d.cu:5-41 — 3x3 / stride 2 / pad 1, OOB taps skipped; int8 NCHW */
+int dlq_maxpool2d_3x3_s2p1_nchw_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, int8_t* y);
+/* K/gap_global.cu:3-33 — per-channel mean; int8 in: y_f32 = (float)sum * fp32(in_scale/HW),
+ * y_i8 = quantise(y_f32, out_scale).  Either output may be NULL. */
+int dlq_gap_global_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, float in_scale, float out_scale,
+                      float* y_f32, int8_t* y_i8);
+/* R/infer_e2e.cu:206-219 fc_forward — int8 W[O,I] (device) x int8 g[N,I] -> int32 ->
+ * logits = fmaf((float)acc, scale[o], bias[o]) */
+int dlq_fc_forward_i8(dlq_ctx* ctx, const int8_t* g, const int8_t* w, const float* scale, const float* bias, int N,
+                      int O, int I, float* logits);
+/* K/softmax.cu:6-47 — row softmax over [N,K] fp32 logits (optional head; uses expf) */
+int dlq_softmax_f32(dlq_ctx* ctx, const float* x, int N, int K, float* y);
+
+/* ------------------------------------------------------------------ whole network
+ * replaces main()'s wiring in R/infer_e2e.cu:254-433 (stem -> layer1..4 -> GAP -> FC) for a batch. */
+#define DLQ_NUM_CONVS 25 /* [0]=stem; block b: [1+3b]=conv1, [2+3b]=conv2, [3+3b]=downsample (NULL if none) */
+#define DLQ_NUM_ACTS 27  /* activation scales: [0]=input, [1]=stem, block b: [2+3b..4+3b]=conv1/ds/out, [26]=gap */
+typedef struct {
+  /* HOST pointers, fp32, the reference's export layout (<key>.bin, tools/export_resnet18.py:85-92) */
+  const float* conv_w[DLQ_NUM_CONVS]; /* OIHW */
+  const float* bn_gamma[DLQ_NUM_CONVS];
+  const float* bn_beta[DLQ_NUM_CONVS];
+  const float* bn_mean[DLQ_NUM_CONVS];
+  const float* bn_var[DLQ_NUM_CONVS];
+  const float* fc_w; /* [1000,512] */
+  const float* fc_b; /* [1000] */
+  float act_scale[DLQ_NUM_ACTS];
+} dlq_resnet18_weights;
+
+int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_batch, dlq_resnet18** out);
+void dlq_resnet18_destroy(dlq_resnet18* m);
+/* x: fp32 NCHW [N,3,224,224] device; logits: fp32 [N,1000] device.  N <= max_batch. */
+int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits);
+/* same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, synchronise */
+int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host);
+/* int8 NCHW copy of an internal checkpoint of the LAST forward: "stem_pool","layer1".."layer4","gap"
+ * (names as R/infer_e2e.cu:297-426 dumps them).  out is a device pointer. */
+int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);
+/* number of kernel launches one forward enqueues (for accounting) */
+int dlq_resnet18_launches(const dlq_resnet18* m);
+
+/* deterministic synthetic data: v[i] = (lo + splitmix64(seed,name) % (hi-lo+1)) * 2^-shift. HOST. */
+void dlq_synth_fill_f32(float* v, size_t n, uint64_t seed, const char* name, int lo, int hi, int shift);
+
+/* ------------------------------------------------------------------ batch-sharded multi-GPU driver
+ * (no reference counterpart: the reference is single-GPU, N=1).  One context + model replica + host
+ * thread per device; images split contiguously; logits gathered into one host array. */
+typedef struct dlq_multi dlq_multi;
+int dlq_multi_create(const int* devices, int n_devices, const dlq_resnet18_weights* w, int max_batch_per_device,
+                     dlq_multi** out);
+void dlq_multi_destroy(dlq_multi* m);
+int dlq_multi_forward_host(dlq_multi* m, const float* x_host, int N, float* logits_host);
+const char* dlq_multi_last_error_string(const dlq_multi* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
