@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py — ResNet-18 INT8 throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+N=1: plain python.  N>1: launched by torch.distributed.run, one rank per GPU; images are batch-sharded
+(weak scaling: every rank processes `batch` images per step), no data-path collective — the only
+cross-rank operations are the timing barrier and the max-reduction of the elapsed time.
+
+A "step" is one pass of the hot path (fp32 NCHW image batch -> int8 quantise -> 20 tcgen05 convs with fused
+epilogue -> max-pool -> GAP+FC -> fp32 logits) over one batch of 256 synthetic images.
+  value   images/s with the input batch resident in HBM (CUDA events on the library's stream)
+  e2e     the same through dlq_resnet18_forward_host: pinned HOST input, H2D copy, forward, D2H of the logits
+  roofline  the conv kernel family (conv_i8_kernel<ROWB>, 20 launches/step): algorithmic int8 ops
+            (3.627 GOP/img) / summed CUDA-event launch durations, against 2 x measured bf16 dense
+  cpu_baseline  the CPU oracle (restatement + QUANT_SPEC; the reference has no CPU ResNet path) on the
+            box's host cores over a bounded sample
+
+--impl reference: the reference arm.  The reference repo contains no CPU (or INT8) implementation of this
+path, so the arm times the CPU oracle port with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONV_GOP_PER_IMG = 3.62712        # 2 x 1813.56 MMAC
+CONV_BYTES_PER_IMG = 5462736      # algorithmic conv bytes/img at B=256
+METRIC = "resnet18_int8_images_per_sec"
+WORKLOAD = "ResNet-18 INT8 (per-channel weight / per-tensor activation), batch 256, 224x224, fused conv epilogue"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.index), "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def shard(total: int, world: int, rank: int):
+    """contiguous batch split used by the multi-GPU driver: rank r takes [r*ceil(total/world), ...)"""
+    per = (total + world - 1) // world
+    lo = min(total, rank * per)
+    return lo, min(total, lo + per)
+
+
+def cpu_oracle_rate(sample_images: int):
+    """images/s of the CPU oracle INT8 forward on `sample_images` synthetic images (all host threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from dlq_b200 import synth
+    w = synth.make_weights(0, fill=orc.fill_f32)
+    m = orc.I8Model(w, synth.load_act_scales(0))
+    x = synth.make_input(0, sample_images, fill=orc.fill_f32)
+    t0 = time.perf_counter()
+    m.forward(x)
+    dt = time.perf_counter() - t0
+    return sample_images / dt, orc.lib().orc_num_threads(), dt
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    from dlq_b200 import synth
+    w = synth.make_weights(0, fill=orc.fill_f32)
+    m = orc.I8Model(w, synth.load_act_scales(0))
+    threads = orc.lib().orc_num_threads()
+    x1 = synth.make_input(0, threads, fill=orc.fill_f32)
+    t0 = time.perf_counter()
+    m.forward(x1)
+    t_probe = (time.perf_counter() - t0) / threads      # seconds per image with all threads busy
+    budget = min(2.0, 150.0 / max(1, args.steps + args.warmup))
+    per_step = max(threads, int(budget / t_probe) // threads * threads)
+    x = synth.make_input(0, per_step, fill=orc.fill_f32)
+    for _ in range(args.warmup):
+        m.forward(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.forward(x)
+    dt = time.perf_counter() - t0
+    val = per_step * args.steps / dt
+    sample = f"{per_step} of {args.batch} images per step (bounded CPU sample), CPU oracle port, OpenMP {threads} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "s8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample,
+                   "note": "the reference repo has no CPU or INT8 implementation of this path (SURVEY §0); "
+                           "this arm is the CPU oracle port"},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+    import dlq_b200
+    from dlq_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.batch
+    ctx = dlq_b200.Context(local_rank)
+    weights = synth.make_weights(0)
+    model = dlq_b200.ResNet18(ctx, weights, synth.load_act_scales(0), B)
+    # every rank gets its own shard of the global synthetic batch (weak scaling: B images per rank)
+    lo, hi = shard(B * world, world, rank)
+    xh_np = synth.make_input(rank, 8)
+    xh = torch.from_numpy(np.ascontiguousarray(np.tile(xh_np, (B // 8 + 1, 1, 1, 1))[:B])).pin_memory()
+    lh = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
+    x = xh.cuda()
+    logits = torch.empty((B, 1000), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        ctx.sync()
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        ctx.sync()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    # ---- device-resident throughput (input batch 154 MB + ~1 GB of activations per step >> 126 MB L2)
+    sampler = ClockSampler(local_rank)
+    ms, clocks = timed(lambda: model.forward(x, logits), args.steps, max(3, args.warmup), sampler)
+    value = B * world * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the host-buffer entry point
+    e2e_steps = max(3, min(args.steps, 20))
+    ms_e2e, _ = timed(lambda: model.forward_host(xh, lh), e2e_steps, 3)
+    e2e_value = B * world * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- per-launch durations (CUDA events between launches on the same stream), conv share -> roofline
+    prof = np.zeros(model.launches, dtype=np.float64)
+    reps = 5
+    model.profile(x, logits)
+    for _ in range(reps):
+        prof += model.profile(x, logits)
+    prof /= reps
+    names = model.LAUNCH_NAMES
+    conv_idx = [i for i, n in enumerate(names) if n not in ("quantize_s2d", "maxpool", "gap_fc")]
+    conv_ms = float(sum(prof[i] for i in conv_idx))
+    peaks, peak_kind = measured_peaks()
+    peak_tops = 2.0 * float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    achieved = CONV_GOP_PER_IMG * B / (conv_ms * 1e-3) / 1e3      # TOP/s
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            rate, threads, dt = cpu_oracle_rate(args.cpu_sample)
+            cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_sample} of {B} images, CPU oracle INT8 forward (restatement + QUANT_SPEC), "
+                             f"{dt:.1f} s; the reference has no CPU ResNet path"}
+        except Exception as ex:   # the oracle is a checker; never let it break the product measurement
+            cpu = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "s8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "sharding": f"batch x{world}",
+                   "l2": "inputs larger than L2 (154 MB fp32 batch + ~1 GB activations per step vs 126 MB L2)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": int(xh.numel() * 4) * world,
+                "d2h_bytes_per_step": int(lh.numel() * 4) * world, "steps": e2e_steps,
+                "note": "pinned host fp32 batch -> H2D -> forward -> D2H logits, every step (PCIe-bound)"},
+        "gpu_launches": int(model.launches * args.steps),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops,
+                     "traffic": traffic, "kernel": "conv_i8_kernel<16|64|128> (20 launches/step)",
+                     "peak_source": f"2 x bf16_tflops_sustained ({peak_kind}); int8 dense = 2 x bf16 on sm_100",
+                     "ops": "int8 MAC*2", "conv_ms_per_step": conv_ms,
+                     "hbm_gbs_conv": CONV_BYTES_PER_IMG * B / (conv_ms * 1e-3) / 1e9,
+                     "per_launch_ms": {n: round(float(v), 4) for n, v in zip(names, prof)}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--cpu-sample", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

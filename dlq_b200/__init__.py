@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
     "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
     "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
-    "dlq_resnet18_checkpoint", "dlq_resnet18_launches", "dlq_synth_fill_f32",
+    "dlq_resnet18_checkpoint", "dlq_resnet18_launches", "dlq_resnet18_profile", "dlq_synth_fill_f32",
     "dlq_multi_create", "dlq_multi_destroy", "dlq_multi_forward_host", "dlq_multi_last_error_string",
 ]
 
@@ -101,6 +101,7 @@ def load_library() -> C.CDLL:
         "dlq_resnet18_forward_host": (i, [vp, vp, i, vp]),
         "dlq_resnet18_checkpoint": (i, [vp, C.c_char_p, vp]),
         "dlq_resnet18_launches": (i, [vp]),
+        "dlq_resnet18_profile": (i, [vp, vp, i, vp, vp]),
         "dlq_synth_fill_f32": (None, [vp, sz, C.c_uint64, C.c_char_p, i, i, i]),
         "dlq_multi_create": (i, [C.POINTER(i), i, C.POINTER(_ResNet18Weights), i, C.POINTER(vp)]),
         "dlq_multi_destroy": (None, [vp]),
@@ -304,6 +305,19 @@ class ResNet18:
     @property
     def launches(self) -> int:
         return self.ctx.lib.dlq_resnet18_launches(self.h)
+
+    LAUNCH_NAMES = (["quantize_s2d", "conv1", "maxpool"]
+                    + [n for b in range(8) for n in
+                       ([f"layer{b // 2 + 1}.{b % 2}.conv1"]
+                        + ([f"layer{b // 2 + 1}.{b % 2}.downsample"] if b in (2, 4, 6) else [])
+                        + [f"layer{b // 2 + 1}.{b % 2}.conv2"])]
+                    + ["gap_fc"])
+
+    def profile(self, x, logits) -> np.ndarray:
+        """per-launch device milliseconds of one forward (CUDA events on the context stream)"""
+        ms = np.zeros(self.launches, dtype=np.float32)
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_profile(self.h, _ptr(x), x.shape[0], _ptr(logits), ms.ctypes.data))
+        return ms
 
     def close(self):
         if self.h:

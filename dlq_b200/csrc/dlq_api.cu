@@ -451,8 +451,7 @@ int dlq_resnet18_launches(const dlq_resnet18* m) {
   return 1 /*quantise+s2d*/ + 20 /*convs*/ + 1 /*max-pool*/ + 1 /*GAP+FC*/;
 }
 
-int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) {
-  if (!m) return DLQ_ERR_ARG;
+static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, cudaEvent_t* ev) {
   dlq_ctx* ctx = m->ctx;
   DLQ_ARG(ctx, x && logits && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
   if (N == 0) return DLQ_OK;
@@ -466,29 +465,68 @@ int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) 
   }
   const dlq_resnet18::Plan& P = *it->second;
   const float* S = m->act_scale;
-  int rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N));
+  int e = 0;
+  auto mark = [&]() -> int {
+    if (ev) DLQ_CUDA(ctx, cudaEventRecord(ev[e++], ctx->stream));
+    return DLQ_OK;
+  };
+  int rc = mark();
   if (rc != DLQ_OK) return rc;
+  rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N));
+  if (rc != DLQ_OK) return rc;
+  if ((rc = mark()) != DLQ_OK) return rc;
   rc = launch_conv(ctx, P.L[0]);
   if (rc != DLQ_OK) return rc;
+  if ((rc = mark()) != DLQ_OK) return rc;
   rc = maxpool_act(ctx, with_n(m->a_stem, N), with_n(m->a_pool, N));
   if (rc != DLQ_OK) return rc;
+  if ((rc = mark()) != DLQ_OK) return rc;
   for (int b = 0; b < 8; ++b) {
     rc = launch_conv(ctx, P.L[1 + 3 * b]);
     if (rc != DLQ_OK) return rc;
+    if ((rc = mark()) != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       rc = launch_conv(ctx, P.L[3 + 3 * b]);
       if (rc != DLQ_OK) return rc;
+      if ((rc = mark()) != DLQ_OK) return rc;
     }
     rc = launch_conv(ctx, P.L[2 + 3 * b]);
     if (rc != DLQ_OK) return rc;
+    if ((rc = mark()) != DLQ_OK) return rc;
   }
   const Act last = with_n(m->a_out[7], N);
   const float s_over_hw = static_cast<float>(static_cast<double>(S[act_out(7)]) / static_cast<double>(last.H * last.W));
   rc = gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
                   logits);
   if (rc != DLQ_OK) return rc;
+  if ((rc = mark()) != DLQ_OK) return rc;
   m->last_N = N;
   return DLQ_OK;
+}
+
+int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) {
+  if (!m) return DLQ_ERR_ARG;
+  return forward_impl(m, x, N, logits, nullptr);
+}
+
+// One forward with a CUDA event between consecutive launches (on the context's stream).
+// ms[i] = device time of launch i, in the order: quantise+s2d, stem conv, max-pool, then per block
+// conv1, [downsample], conv2, and finally GAP+FC  (dlq_resnet18_launches() entries).  Synchronises.
+int dlq_resnet18_profile(dlq_resnet18* m, const float* x, int N, float* logits, float* ms) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, ms != nullptr, "null pointer");
+  const int L = dlq_resnet18_launches(m);
+  std::vector<cudaEvent_t> ev(L + 1);
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  for (auto& e : ev) DLQ_CUDA(ctx, cudaEventCreate(&e));
+  int rc = forward_impl(m, x, N, logits, ev.data());
+  if (rc == DLQ_OK) {
+    DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < L; ++i) DLQ_CUDA(ctx, cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {

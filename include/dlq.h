@@ -136,6 +136,10 @@ int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float
 int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);
 /* number of kernel launches one forward enqueues (for accounting) */
 int dlq_resnet18_launches(const dlq_resnet18* m);
+/* one forward with a CUDA event between launches; ms[dlq_resnet18_launches()] receives each launch's device
+ * time in order: quantise+s2d, stem conv, max-pool, per block conv1,[downsample],conv2, GAP+FC.  Synchronises.
+ * (the reference brackets every launch with its cudaEvent Timer the same way, R/utils.hpp:85-92) */
+int dlq_resnet18_profile(dlq_resnet18* m, const float* x, int N, float* logits, float* ms);
 
 /* deterministic synthetic data: v[i] = (lo + splitmix64(seed,name) % (hi-lo+1)) * 2^-shift. HOST. */
 void dlq_synth_fill_f32(float* v, size_t n, uint64_t seed, const char* name, int lo, int hi, int shift);
