@@ -32,7 +32,8 @@ ACT_INPUT, ACT_STEM, ACT_GAP = 0, 1, 26
 ABI_SYMBOLS = [
     "dlq_create", "dlq_destroy", "dlq_last_error_string", "dlq_sync", "dlq_stream", "dlq_set_stream", "dlq_version",
     "dlq_quantize_f32_i8", "dlq_dequantize_i8_f32", "dlq_dequantize_i8_f32_per_channel",
-    "dlq_conv_weights_pack", "dlq_conv_weights_pack_i8", "dlq_conv_weights_free", "dlq_conv2d_i8",
+    "dlq_conv_weights_pack", "dlq_conv_weights_pack_i8", "dlq_conv_weights_free", "dlq_conv2d_i8", "dlq_fold_bn",
+    "dlq_res_mul",
     "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
     "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
     "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
@@ -48,8 +49,8 @@ class DlqError(RuntimeError):
 
 
 class _Epilogue(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_scale", C.c_float),
-                ("relu", C.c_int), ("out_scale", C.c_float)]
+    _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_mul", C.c_float),
+                ("relu", C.c_int)]
 
 
 class _ResNet18Weights(C.Structure):
@@ -86,6 +87,8 @@ def load_library() -> C.CDLL:
         "dlq_conv_weights_pack_i8": (i, [vp, vp, i, i, i, i, i, i, i, i, C.POINTER(vp)]),
         "dlq_conv_weights_free": (None, [vp]),
         "dlq_conv2d_i8": (i, [vp, vp, i, i, i, i, vp, C.POINTER(_Epilogue), vp, vp, C.POINTER(i), C.POINTER(i)]),
+        "dlq_fold_bn": (None, [vp, vp, vp, vp, f, vp, f, f, i, vp, vp]),
+        "dlq_res_mul": (f, [f, f]),
         "dlq_bn_inference_f32": (i, [vp, vp, vp, vp, vp, vp, f, i, i, i, i]),
         "dlq_relu_forward_f32": (i, [vp, vp, sz]),
         "dlq_relu_forward_i8": (i, [vp, vp, sz]),
@@ -129,6 +132,21 @@ def synth_fill_f32(shape, seed: int, name: str, lo: int, hi: int, shift: int) ->
     a = np.empty(shape, dtype=np.float32)
     lib.dlq_synth_fill_f32(a.ctypes.data, a.size, seed, name.encode(), lo, hi, shift)
     return a
+
+
+def fold_bn(g, b, m, v, s_w, s_x: float, s_y: float, eps: float = 1e-5):
+    """host: (alpha, beta) requantisation constants per QUANT_SPEC §3"""
+    lib = load_library()
+    arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (g, b, m, v, s_w)]
+    oc = arrs[0].size
+    alpha, beta = np.empty(oc, np.float32), np.empty(oc, np.float32)
+    lib.dlq_fold_bn(arrs[0].ctypes.data, arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, eps,
+                    arrs[4].ctypes.data, s_x, s_y, oc, alpha.ctypes.data, beta.ctypes.data)
+    return alpha, beta
+
+
+def res_mul(s_r: float, s_y: float) -> float:
+    return float(load_library().dlq_res_mul(s_r, s_y))
 
 
 class ConvWeights:
@@ -205,10 +223,11 @@ class Context:
                                                    C.byref(h)))
         return ConvWeights(self, h, None, oc)
 
-    def conv2d_i8(self, x, w: ConvWeights, alpha=None, beta=None, residual=None, res_scale: float = 0.0,
-                  relu: bool = False, out_scale: float = 1.0, y=None, acc_out=None):
+    def conv2d_i8(self, x, w: ConvWeights, alpha=None, beta=None, residual=None, res_mul: float = 0.0,
+                  relu: bool = False, y=None, acc_out=None):
+        """alpha/beta/res_mul are requantisation multipliers (output scale folded in, see fold_bn)."""
         n, c, hh, ww = x.shape
-        ep = _Epilogue(_ptr(alpha), _ptr(beta), _ptr(residual), res_scale, int(relu), out_scale)
+        ep = _Epilogue(_ptr(alpha), _ptr(beta), _ptr(residual), res_mul, int(relu))
         oh, ow = C.c_int(), C.c_int()
         self._ck(self.lib.dlq_conv2d_i8(self.h, _ptr(x), n, c, hh, ww, w.handle,
                                         C.byref(ep) if alpha is not None else None, _ptr(y), _ptr(acc_out),

@@ -34,10 +34,6 @@ constexpr int kMaxSteps = 40;    // K steps (tap x channel-block) per conv
 constexpr int kMaxPlanes = 4;
 constexpr int kTileM = 128;
 
-struct ConvStep {
-  uint32_t a_off;    // byte offset of this step's A view inside its sub-patch (= tap shift * ROWB)
-};
-
 struct ConvKernelParams {
   // virtual output space
   int Wp, Wo, Ho, Pv, N;
@@ -57,23 +53,29 @@ struct ConvKernelParams {
   int16_t sub_step0[17];  //   first K step of each sub-patch (sub_step0[n_sub] = n_steps)
   // K steps
   int n_steps;
-  int k32_per_step;       // MMAs (K=32) per step per tile
-  ConvStep steps[kMaxSteps];
+  uint16_t step_a16[kMaxSteps];   // A view offset of each step inside its sub-patch, in 16-byte units (tap shift * ROWB / 16)
   int a_stages, b_stages, acc_stages;
   uint32_t step_bytes;    // weight image bytes per step (n_tile * ROWB, or n_tile*32 for the stem)
   const uint8_t* wimg;    // [n_tiles][n_steps][step_bytes] pre-swizzled smem images
-  // epilogue
-  const float* alpha;     // [OC]
+  // epilogue:  y = clamp(rne(fmaf(r, res_mul, fmaf(acc, alpha[oc], beta[oc]))), lo, 127)
+  const float* alpha;     // [OC] requantisation multiplier (output scale folded in)
   const float* beta;      // [OC]
   const int8_t* residual; // row-padded NHWC int8 [.,Ho,Wo,OC] or nullptr
   int res_PR;
-  float res_scale;
-  int relu;
-  float inv_out_scale;
+  float res_mul;
+  int relu;               // lo = relu ? 0 : -128
   int8_t* out;            // row-padded NHWC int8
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
 };
+
+__device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
+  // cvt.pack.sat.s8.s32.b32 d, a, b, c :  d[7:0] = sat8(b), d[15:8] = sat8(a), d[31:16] = c[15:0]
+  uint32_t hi, r;
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+  return r;   // bytes (low->high): a, b, c, d
+}
 
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha,beta: 2*n_tile f32]
@@ -86,6 +88,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   constexpr uint32_t A_SBO = ROWB == 16 ? 128u : 8u * ROWB;
   constexpr uint32_t A_LBO = ROWB == 16 ? 16u : 0u;
   constexpr uint32_t B_SBO = ROWB == 16 ? 128u : 8u * ROWB;
+  constexpr int K32 = ROWB == 16 ? 1 : ROWB / 32;      // MMAs (K = 32) per step per tile
+  constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -136,78 +140,86 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
     if (elect_one()) {
-      uint32_t a_it = 0;
+      uint32_t as = 0, aph = 0;
       for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
-        const int g0 = st * super_pos;
-        const int v0 = g0 / p.Wp;
+        const int v0 = (st * super_pos) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
-          const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1u;
           mbar_wait(&a_empty[as], aph ^ 1u);
           mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
           tma_load_3d(sA + static_cast<size_t>(as) * a_stage_bytes, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
                       p.row_mul * v0 + p.sub_row_off[s]);
-          ++a_it;
+          if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }
       }
     }
   } else if (warp == 2) {
     // ===================================================================== B (weight step) producer
     if (elect_one()) {
-      uint32_t b_it = 0;
+      uint32_t bs = 0, bph = 0;
       const uint8_t* wsrc = p.wimg + static_cast<size_t>(n_blk) * p.n_steps * p.step_bytes;
       for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
         for (int k = 0; k < p.n_steps; ++k) {
-          const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1u;
           mbar_wait(&b_empty[bs], bph ^ 1u);
           mbar_expect_tx(&b_full[bs], p.step_bytes);
           bulk_g2s(sB + static_cast<size_t>(bs) * b_stage_bytes, wsrc + static_cast<size_t>(k) * p.step_bytes,
                    p.step_bytes, &b_full[bs]);
-          ++b_it;
+          if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (elect_one()) {
-      const uint32_t idesc = umma_idesc_s8(kTileM, static_cast<uint32_t>(p.n_tile));
-      uint32_t a_it = 0, b_it = 0, c_it = 0;
-      for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
-        const int g0 = st * super_pos;
-        const int v0 = g0 / p.Wp;
-        const uint32_t in_patch = static_cast<uint32_t>(g0 - v0 * p.Wp);    // first position's offset in the patch
-        const uint32_t cs = c_it % p.acc_stages, cph = (c_it / p.acc_stages) & 1u;
-        mbar_wait(&acc_empty[cs], cph ^ 1u);
-        const uint32_t d_base = tmem_base + cs * acc_cols;
-        for (int s = 0; s < p.n_sub; ++s) {
-          const uint32_t as = a_it % p.a_stages, aph = (a_it / p.a_stages) & 1u;
-          mbar_wait(&a_full[as], aph);
+    // The whole warp walks the loop (so the address arithmetic stays warp-uniform); one elected lane
+    // issues.  Descriptors are advanced by adding to their low word (start address >> 4).
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_s8(kTileM, static_cast<uint32_t>(p.n_tile));
+    const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT) >> 32);
+    const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, B_SBO, LAYOUT) >> 32);
+    const uint32_t a_lo_flags = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT));
+    const uint32_t b_lo_flags =
+        static_cast<uint32_t>(umma_smem_desc(0, ROWB == 16 ? static_cast<uint32_t>(p.n_tile) * 16u : 0u, B_SBO, LAYOUT));
+    uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+    for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
+      const int g0 = st * super_pos;
+      const int v0 = g0 / p.Wp;
+      const uint32_t in_patch16 = static_cast<uint32_t>(g0 - v0 * p.Wp) * (ROWB / 16);   // first position's offset
+      mbar_wait(&acc_empty[cs], cph ^ 1u);
+      const uint32_t d_base = tmem_base + cs * acc_cols;
+      for (int s = 0; s < p.n_sub; ++s) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        const uint32_t a_lo_base =
+            a_lo_flags + (smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) >> 4) + in_patch16;
+        const int k_end = p.sub_step0[s + 1];
+        for (int k = p.sub_step0[s]; k < k_end; ++k) {
+          mbar_wait(&b_full[bs], bph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) + in_patch * ROWB;
-          for (int k = p.sub_step0[s]; k < p.sub_step0[s + 1]; ++k) {
-            const uint32_t bs = b_it % p.b_stages, bph = (b_it / p.b_stages) & 1u;
-            mbar_wait(&b_full[bs], bph);
-            tc_fence_after();
-            const uint32_t b_addr = smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes);
-            const uint32_t a_step = a_base + p.steps[k].a_off;
+          if (leader) {
+            const uint32_t b_lo = b_lo_flags + (smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes) >> 4);
+            uint32_t a_lo = a_lo_base + p.step_a16[k];
+            uint32_t d = d_base;
             for (int mt = 0; mt < p.MT; ++mt) {
-              const uint32_t a_tile = a_step + static_cast<uint32_t>(mt) * kTileM * ROWB;
-              for (int kk = 0; kk < p.k32_per_step; ++kk) {
-                const uint64_t ad = umma_smem_desc(a_tile + kk * 32u, A_LBO, A_SBO, LAYOUT);
-                const uint64_t bd =
-                    ROWB == 16 ? umma_smem_desc(b_addr, static_cast<uint32_t>(p.n_tile) * 16u, B_SBO, LAYOUT)
-                               : umma_smem_desc(b_addr + kk * 32u, 0u, B_SBO, LAYOUT);
-                umma_i8(d_base + static_cast<uint32_t>(mt) * p.n_tile, ad, bd, idesc, (k | kk) ? 1u : 0u);
+#pragma unroll
+              for (int kk = 0; kk < K32; ++kk) {
+                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
+                const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + (ROWB == 16 ? 0u : 2u * kk));
+                umma_i8(d, ad, bd, idesc, (k | kk) ? 1u : 0u);
               }
+              a_lo += TILE16;
+              d += static_cast<uint32_t>(p.n_tile);
             }
             umma_commit(&b_empty[bs]);   // weight stage free once these MMAs retire
-            ++b_it;
           }
-          umma_commit(&a_empty[as]);     // sub-patch stage free
-          ++a_it;
+          __syncwarp();
+          if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
         }
-        umma_commit(&acc_full[cs]);      // accumulators ready for the epilogue
-        ++c_it;
+        if (leader) umma_commit(&a_empty[as]);     // sub-patch stage free
+        __syncwarp();
+        if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
       }
+      if (leader) umma_commit(&acc_full[cs]);      // accumulators ready for the epilogue
+      __syncwarp();
+      if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
@@ -215,15 +227,15 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int n_groups = n_epi_warps >> 2;              // 1 or 2 column groups
     const int grp = (ew >> 2);                          // which column group this warp handles
-    const int cols_per_grp = p.n_tile / n_groups;
+    const int cols_per_grp = p.n_tile / n_groups;       // multiple of 32
     const int col_lo = grp * cols_per_grp;
     const int row = quarter * 32 + lane;                // accumulator row within the tile
     const bool has_res = p.residual != nullptr;
     const int out_pitch = p.Ho + p.out_PR, res_pitch = p.Ho + p.res_PR;
-    const int lo = p.relu ? 0 : -128;
-    uint32_t c_it = 0;
+    const uint32_t relu_floor = p.relu ? 0u : 0x80808080u;   // per-byte signed max with 0 (ReLU) or -128 (no-op)
+    const float res_mul = p.res_mul;
+    uint32_t cs = 0, cph = 0;
     for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
-      const uint32_t cs = c_it % p.acc_stages, cph = (c_it / p.acc_stages) & 1u;
       mbar_wait(&acc_full[cs], cph);
       tc_fence_after();
       for (int mt = 0; mt < p.MT; ++mt) {
@@ -233,38 +245,52 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
         const bool valid = (x < p.Wo) && (r < p.Ho) && (n < p.N);
         const size_t opix = (static_cast<size_t>(p.out_PR + n * out_pitch + r) * p.Wo + x);
         const size_t rpix = (static_cast<size_t>(p.res_PR + n * res_pitch + r) * p.Wo + x);
-        const size_t dpix = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
         const uint32_t taddr = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile +
                                (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int c = col_lo; c < col_lo + cols_per_grp; c += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + c, v);
+        for (int c = col_lo; c < col_lo + cols_per_grp; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          int4 rv[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+          if (has_res && valid) {
+            const int4* rp = reinterpret_cast<const int4*>(p.residual + rpix * p.OC + n0 + c);
+            rv[0] = __ldg(rp);
+            rv[1] = __ldg(rp + 1);
+          }
           tmem_ld_wait();
           if (valid) {
             if (p.acc_out) {
+              const size_t dpix = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
               int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix * p.OC + n0 + c);
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
+              for (int j = 0; j < 8; ++j)
                 dst[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
             }
             if (p.out) {
-              int4 rv = make_int4(0, 0, 0, 0);
-              if (has_res) rv = __ldg(reinterpret_cast<const int4*>(p.residual + rpix * p.OC + n0 + c));
-              const int8_t* rb = reinterpret_cast<const int8_t*>(&rv);
-              uint32_t packed[4];
+              const float4* a4 = reinterpret_cast<const float4*>(s_alpha + c);
+              const float4* b4 = reinterpret_cast<const float4*>(s_beta + c);
+              const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+              uint32_t packed[8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float t = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[j])), s_alpha[c + j], s_beta[c + j]);
-                if (has_res) t = __fmaf_rn(static_cast<float>(rb[j]), p.res_scale, t);
-                if (p.relu && t < 0.f) t = 0.f;
-                t = __fmul_rn(t, p.inv_out_scale);
-                int q = __float2int_rn(t);
-                q = max(lo, min(127, q));
-                if ((j & 3) == 0) packed[j >> 2] = 0;
-                packed[j >> 2] |= (static_cast<uint32_t>(q) & 0xFFu) << (8 * (j & 3));
+              for (int j = 0; j < 8; ++j) {
+                const float4 al = a4[j], be = b4[j];
+                float t0 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 0])), al.x, be.x);
+                float t1 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 1])), al.y, be.y);
+                float t2 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 2])), al.z, be.z);
+                float t3 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 3])), al.w, be.w);
+                if (has_res) {
+                  const uint32_t w = rw[j];
+                  t0 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w)), res_mul, t0);
+                  t1 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 8)), res_mul, t1);
+                  t2 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 16)), res_mul, t2);
+                  t3 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 24)), res_mul, t3);
+                }
+                const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2),
+                                                 __float2int_rn(t3));
+                packed[j] = __vmaxs4(q, relu_floor);
               }
-              *reinterpret_cast<int4*>(p.out + opix * p.OC + n0 + c) =
-                  make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
+              int4* dst = reinterpret_cast<int4*>(p.out + opix * p.OC + n0 + c);
+              dst[0] = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
+              dst[1] = make_int4((int)packed[4], (int)packed[5], (int)packed[6], (int)packed[7]);
             }
           }
         }
@@ -272,7 +298,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[cs]);
-      ++c_it;
+      if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
   }
   tc_fence_before();

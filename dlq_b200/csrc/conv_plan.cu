@@ -175,8 +175,7 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
 }
 
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
-              const float* beta, const Act* residual, float res_scale, int relu, float out_scale, int32_t* acc_out,
-              ConvLaunch* L) {
+              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L) {
   ConvKernelParams& p = L->p;
   memset(&p, 0, sizeof(p));
   const int rowb = w->rowb;
@@ -224,13 +223,12 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   make_schedule(w, subs, steps);
   p.n_sub = static_cast<int>(subs.size());
   p.n_steps = static_cast<int>(steps.size());
-  p.k32_per_step = w->kind == CONV_STEM ? 1 : rowb / 32;
   p.step_bytes = w->step_bytes;
   p.wimg = w->d_img;
   int maxshift = 0;
   for (int k = 0; k < p.n_steps; ++k) {
     const int sh = steps[k].da * p.Wp + steps[k].db;
-    p.steps[k].a_off = static_cast<uint32_t>(sh) * rowb;
+    p.step_a16[k] = static_cast<uint16_t>(sh * rowb / 16);
     maxshift = std::max(maxshift, sh + (w->kind == CONV_STEM ? 1 : 0));
   }
   for (int s = 0; s < p.n_sub; ++s) {
@@ -274,9 +272,8 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.beta = beta;
   p.residual = residual ? residual->ptr : nullptr;
   p.res_PR = residual ? residual->PR : 0;
-  p.res_scale = res_scale;
+  p.res_mul = res_mul;
   p.relu = relu;
-  p.inv_out_scale = inv_scale(out_scale);
   p.out = out.ptr;
   p.out_PR = out.PR;
   p.acc_out = acc_out;

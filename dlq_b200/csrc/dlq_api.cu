@@ -123,6 +123,18 @@ void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std:
 
 }  // namespace
 
+extern "C" {
+void dlq_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, const float* s_w,
+                 float s_x, float s_y, int OC, float* alpha, float* beta) {
+  for (int oc = 0; oc < OC; ++oc) {
+    const double a = static_cast<double>(g[oc]) / std::sqrt(static_cast<double>(v[oc]) + static_cast<double>(eps));
+    alpha[oc] = static_cast<float>(static_cast<double>(s_x) * static_cast<double>(s_w[oc]) * a / static_cast<double>(s_y));
+    beta[oc] = static_cast<float>((static_cast<double>(b[oc]) - static_cast<double>(m[oc]) * a) / static_cast<double>(s_y));
+  }
+}
+float dlq_res_mul(float s_r, float s_y) { return static_cast<float>(static_cast<double>(s_r) / static_cast<double>(s_y)); }
+}
+
 // ================================================================================================
 // per-layer convolution
 // ================================================================================================
@@ -171,8 +183,8 @@ int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, con
                   const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW) {
   if (!ctx) return DLQ_ERR_ARG;
   DLQ_ARG(ctx, x && w && N >= 0 && C == w->IC && H > 0 && W > 0, "null pointer or dims do not match the packed weights");
-  DLQ_ARG(ctx, (y == nullptr) || (ep != nullptr && ep->alpha && ep->beta && ep->out_scale > 0.f),
-          "an int8 output needs an epilogue with alpha, beta and a positive out_scale");
+  DLQ_ARG(ctx, (y == nullptr) || (ep != nullptr && ep->alpha && ep->beta),
+          "an int8 output needs an epilogue with alpha and beta");
   DLQ_ARG(ctx, y || acc_out, "no output requested");
   int oh, ow;
   conv_out_dims(w, H, W, &oh, &ow);
@@ -215,7 +227,7 @@ int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, con
   }
   ConvLaunch L;
   rc = plan_conv(ctx, w, in, out, ep ? ep->alpha : nullptr, ep ? ep->beta : nullptr, has_res ? &res : nullptr,
-                 ep ? ep->res_scale : 0.f, ep ? ep->relu : 0, ep ? ep->out_scale : 1.f, acc_nhwc, &L);
+                 ep ? ep->res_mul : 0.f, ep ? ep->relu : 0, acc_nhwc, &L);
   if (rc != DLQ_OK) return rc;
   rc = launch_conv(ctx, L);
   if (rc != DLQ_OK) return rc;
@@ -305,26 +317,24 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   P->N = N;
   const float* S = m->act_scale;
   int rc = plan_conv(ctx, m->conv[0], with_n(m->a_in, N), with_n(m->a_stem, N), m->d_alpha[0], m->d_beta[0], nullptr, 0.f, 1,
-                     S[kActStem], nullptr, &P->L[0]);
+                     nullptr, &P->L[0]);
   if (rc != DLQ_OK) return rc;
   Act cur = with_n(m->a_pool, N);
   float s_cur = S[kActStem];
   for (int b = 0; b < 8; ++b) {
     const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, id = 3 + 3 * b;
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
-    rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, S[act_c1(b)], nullptr,
-                   &P->L[i1]);
+    rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1]);
     if (rc != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       Act ds = with_n(m->a_ds[b], N);
-      rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, S[act_ds(b)], nullptr,
-                     &P->L[id]);
+      rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, nullptr, &P->L[id]);
       if (rc != DLQ_OK) return rc;
-      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &ds, S[act_ds(b)], 1, S[act_out(b)], nullptr,
-                     &P->L[i2]);
+      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &ds, dlq_res_mul(S[act_ds(b)], S[act_out(b)]), 1,
+                     nullptr, &P->L[i2]);
     } else {
-      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &cur, s_cur, 1, S[act_out(b)], nullptr,
-                     &P->L[i2]);
+      rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &cur, dlq_res_mul(s_cur, S[act_out(b)]), 1,
+                     nullptr, &P->L[i2]);
     }
     if (rc != DLQ_OK) return rc;
     cur = o;
@@ -361,16 +371,16 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   std::copy(w->act_scale, w->act_scale + DLQ_NUM_ACTS, m->act_scale);
 
   // ---- convs: geometry as wired by runtime/infer_e2e.cu:258-407
-  struct CG { int ic, oc, k, s, p; float s_in; };
+  struct CG { int ic, oc, k, s, p; float s_in, s_out; };
   CG geo[DLQ_NUM_CONVS];
-  geo[0] = {3, 64, 7, 2, 3, w->act_scale[kActInput]};
+  geo[0] = {3, 64, 7, 2, 3, w->act_scale[kActInput], w->act_scale[kActStem]};
   {
     float s_cur = w->act_scale[kActStem];
     for (int b = 0; b < 8; ++b) {
       const BlockCfg& B = kBlocks[b];
-      geo[1 + 3 * b] = {B.ic, B.oc, 3, B.stride, 1, s_cur};
-      geo[2 + 3 * b] = {B.oc, B.oc, 3, 1, 1, w->act_scale[act_c1(b)]};
-      geo[3 + 3 * b] = {B.ic, B.oc, 1, B.stride, 0, s_cur};
+      geo[1 + 3 * b] = {B.ic, B.oc, 3, B.stride, 1, s_cur, w->act_scale[act_c1(b)]};
+      geo[2 + 3 * b] = {B.oc, B.oc, 3, 1, 1, w->act_scale[act_c1(b)], w->act_scale[act_out(b)]};
+      geo[3 + 3 * b] = {B.ic, B.oc, 1, B.stride, 0, s_cur, w->act_scale[act_ds(b)]};
       s_cur = w->act_scale[act_out(b)];
     }
   }
@@ -382,13 +392,10 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     std::vector<float> s_w(g.oc);
     int rc = dlq_conv_weights_pack(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i]);
     if (rc != DLQ_OK) return rc;
-    // folded constants, QUANT_SPEC §3: a = gamma / sqrt(var + eps) in double, rounded once
+    // folded constants, QUANT_SPEC §3 (double arithmetic, rounded once)
     std::vector<float> alpha(g.oc), beta(g.oc);
-    for (int oc = 0; oc < g.oc; ++oc) {
-      const double a = static_cast<double>(w->bn_gamma[i][oc]) / std::sqrt(static_cast<double>(w->bn_var[i][oc]) + static_cast<double>(1e-5f));
-      alpha[oc] = static_cast<float>(static_cast<double>(g.s_in) * static_cast<double>(s_w[oc]) * a);
-      beta[oc] = static_cast<float>(static_cast<double>(w->bn_beta[i][oc]) - static_cast<double>(w->bn_mean[i][oc]) * a);
-    }
+    dlq_fold_bn(w->bn_gamma[i], w->bn_beta[i], w->bn_mean[i], w->bn_var[i], 1e-5f, s_w.data(), g.s_in, g.s_out, g.oc,
+                alpha.data(), beta.data());
     rc = upload(m.get(), alpha, &m->d_alpha[i]);
     if (rc != DLQ_OK) return rc;
     rc = upload(m.get(), beta, &m->d_beta[i]);

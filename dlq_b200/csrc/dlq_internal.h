@@ -88,8 +88,7 @@ struct ConvLaunch {
 };
 // Build the launch for conv `w` reading `in` and writing `out` (either of out.ptr / acc_out may be null).
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
-              const float* beta, const Act* residual, float res_scale, int relu, float out_scale, int32_t* acc_out,
-              ConvLaunch* L);
+              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L);
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L);
 void conv_out_dims(const dlq_conv_weights* w, int H, int W, int* OH, int* OW);
 

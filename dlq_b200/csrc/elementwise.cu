@@ -278,31 +278,51 @@ __global__ void maxpool_nchw_i8_kernel(const int8_t* __restrict__ x, int8_t* __r
 // once per CTA, each warp producing one output row for all IMG images with dp4a + warp shuffles.
 // (semantics: K/gap_global.cu:10-32 mean, R/infer_e2e.cu:206-219 FC + bias; arithmetic QUANT_SPEC §5)
 // ------------------------------------------------------------------------------------------------
-constexpr int kGapImgs = 8;
+constexpr int kGapImgs = 4;
+constexpr int kGapParts = 4;
 __global__ void __launch_bounds__(512)
 gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
               float inv_gap_scale, const int8_t* __restrict__ fc_w, const float* __restrict__ fc_scale,
               const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits) {
-  extern __shared__ int8_t sg[];   // [kGapImgs][C]
+  extern __shared__ int4 smem_gap[];
+  int32_t* part_sum = reinterpret_cast<int32_t*>(smem_gap);                                 // [imgs][parts][C]
+  int8_t* sg = reinterpret_cast<int8_t*>(part_sum + kGapImgs * kGapParts * C);              // [imgs][C]
   const int n0 = blockIdx.x * kGapImgs;
   const int nimg = min(kGapImgs, N - n0);
   const int HW = H * W;
-  for (int i = threadIdx.x; i < nimg * (C / 4); i += blockDim.x) {
-    const int im = i / (C / 4), c4 = i % (C / 4);
-    const size_t row0 = static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR);
-    const int8_t* src = in + row0 * W * C + c4 * 4;
-    int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    for (int px = 0; px < HW; ++px) {
-      const char4 v = *reinterpret_cast<const char4*>(src + static_cast<size_t>(px) * C);
-      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+  {
+    // phase 1a: thread = (image, pixel partition, 16-channel group); 16-byte loads, all independent
+    const int im = threadIdx.x >> 7, part = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
+    if (im < nimg) {
+      const size_t row0 = static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR);
+      for (int cg = lane; cg < C / 16; cg += 32) {
+        const int8_t* src = in + row0 * W * C + cg * 16;
+        int acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0;
+#pragma unroll 4
+        for (int px = part; px < HW; px += kGapParts) {
+          const int4 v = __ldg(reinterpret_cast<const int4*>(src + static_cast<size_t>(px) * C));
+          const int8_t* b = reinterpret_cast<const int8_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] += b[j];
+        }
+        int32_t* dst = part_sum + (im * kGapParts + part) * C + cg * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[j] = acc[j];
+      }
     }
-    const int q0 = quant_rn(__fmul_rn(__fmul_rn((float)s0, scale_over_hw), inv_gap_scale), -128, 127);
-    const int q1 = quant_rn(__fmul_rn(__fmul_rn((float)s1, scale_over_hw), inv_gap_scale), -128, 127);
-    const int q2 = quant_rn(__fmul_rn(__fmul_rn((float)s2, scale_over_hw), inv_gap_scale), -128, 127);
-    const int q3 = quant_rn(__fmul_rn(__fmul_rn((float)s3, scale_over_hw), inv_gap_scale), -128, 127);
-    const uint32_t pk = pack4(q0, q1, q2, q3);
-    reinterpret_cast<uint32_t*>(sg + im * C)[c4] = pk;
-    if (gap_q) reinterpret_cast<uint32_t*>(gap_q + static_cast<size_t>(n0 + im) * C)[c4] = pk;
+  }
+  __syncthreads();
+  // phase 1b: reduce the partitions, scale, requantise (QUANT_SPEC §5)
+  for (int i = threadIdx.x; i < nimg * C; i += blockDim.x) {
+    const int im = i / C, c = i - im * C;
+    int s = 0;
+#pragma unroll
+    for (int pt = 0; pt < kGapParts; ++pt) s += part_sum[(im * kGapParts + pt) * C + c];
+    const int q = quant_rn(__fmul_rn(__fmul_rn((float)s, scale_over_hw), inv_gap_scale), -128, 127);
+    sg[im * C + c] = static_cast<int8_t>(q);
+    if (gap_q) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
   }
   __syncthreads();
   if (!logits) return;
@@ -522,7 +542,8 @@ int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_s
   DLQ_ARG(ctx, in.C % 512 == 0 || in.C % 16 == 0, "gap channels");
   DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
   const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
-  gap_fc_kernel<<<blocks, 512, kGapImgs * in.C, ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
+  const size_t gap_smem = static_cast<size_t>(kGapImgs) * kGapParts * in.C * 4 + static_cast<size_t>(kGapImgs) * in.C;
+  gap_fc_kernel<<<blocks, 512, gap_smem, ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
                                                                inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;

@@ -66,17 +66,28 @@ int dlq_conv_weights_pack_i8(dlq_ctx* ctx, const int8_t* wq_oihw_host, int OC, i
                              int sW, int pH, int pW, dlq_conv_weights** out);
 void dlq_conv_weights_free(dlq_conv_weights* w);
 
-/* Fused epilogue, QUANT_SPEC §3 (each line one binary32 rounding):
- *   t = fmaf((float)acc, alpha[oc], beta[oc]);  if (residual) t = fmaf((float)r, res_scale, t);
- *   if (relu && t < 0) t = 0;  t *= fp32(1/out_scale);  y = clamp(rne(t), relu ? 0 : -128, 127)   */
+/* Fused epilogue, QUANT_SPEC §3 (requantisation-multiplier form; each line one binary32 rounding):
+ *   t = fmaf((float)acc, alpha[oc], beta[oc]);
+ *   if (residual) t = fmaf((float)r, res_mul, t);
+ *   y = clamp(rne(t), relu ? 0 : -128, 127)           (ReLU == the lower clamp at 0)
+ * with the output scale already folded in by the caller:
+ *   alpha[oc] = s_x*s_w[oc]*gamma/sqrt(var+eps)/s_y,  beta[oc] = (beta_bn - mean*gamma/sqrt(var+eps))/s_y,
+ *   res_mul = s_r/s_y      -- dlq_fold_bn() computes alpha/beta exactly as the spec prescribes. */
 typedef struct {
   const float* alpha;     /* [OC] device */
   const float* beta;      /* [OC] device */
   const int8_t* residual; /* NCHW int8 [N,OC,OH,OW] device, or NULL */
-  float res_scale;
+  float res_mul;
   int relu;
-  float out_scale;
 } dlq_epilogue;
+
+/* HOST helper: folded BN + requantisation constants (double arithmetic, rounded once to fp32; QUANT_SPEC §3).
+ * g/b/m/v: BN gamma/beta/running_mean/running_var [OC]; s_w: per-channel weight scales [OC];
+ * s_x / s_y: input / output activation scales.  Replaces bn_launch's per-call uploads (R/infer_e2e.cu:83-97). */
+void dlq_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, const float* s_w,
+                 float s_x, float s_y, int OC, float* alpha_host, float* beta_host);
+/* HOST helper: fp32(s_r / s_y) */
+float dlq_res_mul(float s_r, float s_y);
 
 /* x: int8 NCHW [N,C,H,W]; y: int8 NCHW [N,OC,OH,OW] (may be NULL); acc_out: int32 NCHW raw accumulators
  * (may be NULL; parity/debug).  OH/OW are returned like the reference's int& OH, int& OW. */

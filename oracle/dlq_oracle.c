@@ -318,21 +318,22 @@ void orc_quantize_weights_per_channel(const float* w, int OC, int K, int8_t* q, 
   }
 }
 void orc_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, const float* s_w,
-                 float s_x, int OC, float* alpha, float* beta) {
+                 float s_x, float s_y, int OC, float* alpha, float* beta) {
   for (int oc = 0; oc < OC; ++oc) {
     const double a = (double)g[oc] / sqrt((double)v[oc] + (double)eps);
-    alpha[oc] = (float)((double)s_x * (double)s_w[oc] * a);
-    beta[oc] = (float)((double)b[oc] - (double)m[oc] * a);
+    alpha[oc] = (float)((double)s_x * (double)s_w[oc] * a / (double)s_y);
+    beta[oc] = (float)(((double)b[oc] - (double)m[oc] * a) / (double)s_y);
   }
 }
+float orc_res_mul(float s_r, float s_y) { return (float)((double)s_r / (double)s_y); }
 
 /* epilogue, QUANT_SPEC §3 — each line is one binary32 rounding */
-static inline int8_t epilogue1(int32_t acc, float alpha, float beta, int has_res, int8_t r, float s_r, int relu,
-                               float inv_s_y) {
+static inline int8_t epilogue1(int32_t acc, float alpha, float beta, int has_res, int8_t r, float res_mul,
+                               int relu) {
   float t = fmaf((float)acc, alpha, beta);
-  if (has_res) t = fmaf((float)r, s_r, t);
-  if (relu && t < 0.f) t = 0.f; /* reference ReLU form, K/relu.cu:9 */
-  t = t * inv_s_y;
+  if (has_res) t = fmaf((float)r, res_mul, t);
+  /* ReLU (reference form `if (x < 0) x = 0`, K/relu.cu:9) commutes with the positive rescale and the
+   * rounding, so it is exactly the lower clamp at 0 */
   return quant1(t, relu ? 0 : -128, 127);
 }
 
@@ -365,7 +366,7 @@ void orc_conv2d_i8(const int8_t* x, int N, int C, int H, int W, const int8_t* w,
           if (acc_out) acc_out[o] = acc;
           if (y && ep)
             y[o] = epilogue1(acc, ep->alpha[oc], ep->beta[oc], ep->residual != NULL,
-                             ep->residual ? ep->residual[o] : 0, ep->res_scale, ep->relu, ep->inv_out_scale);
+                             ep->residual ? ep->residual[o] : 0, ep->res_mul, ep->relu);
         }
     }
 }
@@ -418,12 +419,12 @@ void orc_fc_i8(const int8_t* g, const int8_t* w, const float* w_scale_times_g, c
     }
 }
 
-static int8_t* convq(const orc_convq* p, const int8_t* x, int N, int H, int W, const int8_t* res, float s_res,
-                     int relu, float s_out, int* OH, int* OW) {
+static int8_t* convq(const orc_convq* p, const int8_t* x, int N, int H, int W, const int8_t* res, float res_mul,
+                     int relu, int* OH, int* OW) {
   *OH = (H + 2 * p->pad - p->k) / p->stride + 1;
   *OW = (W + 2 * p->pad - p->k) / p->stride + 1;
   int8_t* y = (int8_t*)malloc((size_t)N * p->oc * (*OH) * (*OW));
-  orc_epilogue ep = {p->alpha, p->beta, res, s_res, relu, orc_inv_scale(s_out)};
+  orc_epilogue ep = {p->alpha, p->beta, res, res_mul, relu};
   orc_conv2d_i8(x, N, p->ic, H, W, p->w, p->oc, p->k, p->k, p->stride, p->stride, p->pad, p->pad, &ep, NULL, y);
   return y;
 }
@@ -435,7 +436,7 @@ void orc_resnet18_i8_forward(const orc_resnet18_i8* m, const float* x, int N, fl
   int H = 224, W = 224, OH, OW;
   int8_t* qx = (int8_t*)malloc((size_t)N * 3 * H * W);
   orc_quantize_f32_i8(x, (size_t)N * 3 * H * W, orc_inv_scale(S[ORC_ACT_INPUT]), -128, 127, qx);
-  int8_t* y0 = convq(&m->convs[0], qx, N, H, W, NULL, 0.f, 1, S[ORC_ACT_STEM], &OH, &OW);
+  int8_t* y0 = convq(&m->convs[0], qx, N, H, W, NULL, 0.f, 1, &OH, &OW);
   free(qx);
   const int PH = (OH + 2 - 3) / 2 + 1, PW = (OW + 2 - 3) / 2 + 1;
   int8_t* cur = (int8_t*)malloc((size_t)N * 64 * PH * PW);
@@ -450,18 +451,17 @@ void orc_resnet18_i8_forward(const orc_resnet18_i8* m, const float* x, int N, fl
     const orc_convq* c1 = &m->convs[1 + 3 * b];
     const orc_convq* c2 = &m->convs[2 + 3 * b];
     const orc_convq* ds = &m->convs[3 + 3 * b];
-    const float s_c1 = S[ORC_ACT_BLOCK0 + 3 * b + 0], s_ds = S[ORC_ACT_BLOCK0 + 3 * b + 1],
-                s_out = S[ORC_ACT_BLOCK0 + 3 * b + 2];
+    const float s_ds = S[ORC_ACT_BLOCK0 + 3 * b + 1], s_out = S[ORC_ACT_BLOCK0 + 3 * b + 2];
     int H1, W1, H2, W2;
-    int8_t* t1 = convq(c1, cur, N, H, W, NULL, 0.f, 1, s_c1, &H1, &W1);
+    int8_t* t1 = convq(c1, cur, N, H, W, NULL, 0.f, 1, &H1, &W1);
     int8_t* t2;
     if (ds->w) {
       int Hd, Wd;
-      int8_t* sk = convq(ds, cur, N, H, W, NULL, 0.f, 0, s_ds, &Hd, &Wd);
-      t2 = convq(c2, t1, N, H1, W1, sk, s_ds, 1, s_out, &H2, &W2);
+      int8_t* sk = convq(ds, cur, N, H, W, NULL, 0.f, 0, &Hd, &Wd);
+      t2 = convq(c2, t1, N, H1, W1, sk, orc_res_mul(s_ds, s_out), 1, &H2, &W2);
       free(sk);
     } else {
-      t2 = convq(c2, t1, N, H1, W1, cur, s_cur, 1, s_out, &H2, &W2);
+      t2 = convq(c2, t1, N, H1, W1, cur, orc_res_mul(s_cur, s_out), 1, &H2, &W2);
     }
     free(t1);
     free(cur);

@@ -94,17 +94,18 @@ void orc_dequantize_i8_f32(const int8_t* q, size_t n, float s, float* x);
 void orc_dequantize_i8_f32_per_channel(const int8_t* q, int N, int C, int HW, const float* s, float* x);
 /* per-output-channel symmetric weight quantisation: s[oc] = absmax/127 (1.0 if the row is all zero) */
 void orc_quantize_weights_per_channel(const float* w, int OC, int K, int8_t* q, float* s);
-/* folded constants (QUANT_SPEC §3): alpha = fp32(s_x*s_w*a), beta = fp32(beta_bn - mean*a) */
+/* folded requantisation constants (QUANT_SPEC §3), a = gamma/sqrt(var+eps), all in double, rounded once:
+ *   alpha = fp32(s_x*s_w*a/s_y), beta = fp32((beta_bn - mean*a)/s_y);  res_mul = fp32(s_r/s_y) */
 void orc_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, const float* s_w,
-                 float s_x, int OC, float* alpha, float* beta);
+                 float s_x, float s_y, int OC, float* alpha, float* beta);
+float orc_res_mul(float s_r, float s_y);
 
 typedef struct {
   const float* alpha;     /* [OC] */
   const float* beta;      /* [OC] */
   const int8_t* residual; /* NCHW int8 or NULL */
-  float res_scale;
+  float res_mul;
   int relu;
-  float inv_out_scale;
 } orc_epilogue;
 
 /* int8 conv; acc_out (int32 NCHW, may be NULL) receives raw accumulators, y (int8 NCHW) the epilogue result */

@@ -31,8 +31,8 @@ class CkF32(C.Structure):
 
 
 class Epilogue(C.Structure):
-    _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_scale", C.c_float),
-                ("relu", C.c_int), ("inv_out_scale", C.c_float)]
+    _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_mul", C.c_float),
+                ("relu", C.c_int)]
 
 
 class ConvQ(C.Structure):
@@ -65,6 +65,8 @@ def lib() -> C.CDLL:
         _lib.orc_inv_scale.restype = C.c_float
         _lib.orc_inv_scale.argtypes = [C.c_float]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_res_mul.restype = C.c_float
+        _lib.orc_res_mul.argtypes = [C.c_float, C.c_float]
     return _lib
 
 
@@ -208,17 +210,20 @@ def quantize_weights(w):
     return q, s
 
 
-def fold_bn(g, b, m, v, s_w, s_x, eps=1e-5):
+def fold_bn(g, b, m, v, s_w, s_x, s_y, eps=1e-5):
     oc = len(s_w)
     alpha = np.empty(oc, dtype=np.float32)
     beta = np.empty(oc, dtype=np.float32)
-    lib().orc_fold_bn(_p(f32(g)), _p(f32(b)), _p(f32(m)), _p(f32(v)), C.c_float(eps), _p(f32(s_w)), C.c_float(s_x), oc,
-                      _p(alpha), _p(beta))
+    lib().orc_fold_bn(_p(f32(g)), _p(f32(b)), _p(f32(m)), _p(f32(v)), C.c_float(eps), _p(f32(s_w)), C.c_float(s_x),
+                      C.c_float(s_y), oc, _p(alpha), _p(beta))
     return alpha, beta
 
 
-def conv2d_i8(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_scale=0.0, relu=False, out_scale=1.0,
-              want_acc=True):
+def res_mul(s_r, s_y) -> float:
+    return float(lib().orc_res_mul(C.c_float(s_r), C.c_float(s_y)))
+
+
+def conv2d_i8(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_mul=0.0, relu=False, want_acc=True):
     """returns (acc int32 NCHW or None, y int8 NCHW or None)"""
     x = np.ascontiguousarray(x, dtype=np.int8)
     wq = np.ascontiguousarray(wq, dtype=np.int8)
@@ -233,7 +238,7 @@ def conv2d_i8(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_scal
         a, b = f32(alpha), f32(beta)
         r = None if residual is None else np.ascontiguousarray(residual, dtype=np.int8)
         keep = [a, b, r]
-        ep = Epilogue(_p(a), _p(b), _p(r), res_scale, int(relu), inv_scale(out_scale))
+        ep = Epilogue(_p(a), _p(b), _p(r), res_mul, int(relu))
     lib().orc_conv2d_i8(_p(x), n, c, h, w, _p(wq), oc, kh, kw, stride, stride, pad, pad,
                         C.byref(ep) if ep is not None else None, _p(acc), _p(y))
     return acc, y
@@ -337,11 +342,12 @@ class I8Model:
         for i in range(NUM_ACTS):
             self.s.act_scale[i] = float(S[i])
         s_in = {0: S[ACT_INPUT]}
+        s_out = {0: S[ACT_STEM]}
         s_cur = S[ACT_STEM]
         for b in range(NUM_BLOCKS):
-            s_in[1 + 3 * b] = s_cur
-            s_in[2 + 3 * b] = S[ACT_BLOCK0 + 3 * b]
-            s_in[3 + 3 * b] = s_cur
+            s_in[1 + 3 * b], s_out[1 + 3 * b] = s_cur, S[ACT_BLOCK0 + 3 * b]
+            s_in[2 + 3 * b], s_out[2 + 3 * b] = S[ACT_BLOCK0 + 3 * b], S[ACT_BLOCK0 + 3 * b + 2]
+            s_in[3 + 3 * b], s_out[3 + 3 * b] = s_cur, S[ACT_BLOCK0 + 3 * b + 1]
             s_cur = S[ACT_BLOCK0 + 3 * b + 2]
         self.wq, self.alpha, self.beta, self.s_w = {}, {}, {}, {}
         for idx in range(NUM_CONVS):
@@ -353,7 +359,7 @@ class I8Model:
             wk, bn = keys[idx]
             q, sw = quantize_weights(weights[wk])
             a, bt = fold_bn(weights[bn + ".weight"], weights[bn + ".bias"], weights[bn + ".running_mean"],
-                            weights[bn + ".running_var"], sw, float(s_in[idx]))
+                            weights[bn + ".running_var"], sw, float(s_in[idx]), float(s_out[idx]))
             self.wq[idx], self.alpha[idx], self.beta[idx], self.s_w[idx] = q, a, bt, sw
             cq.ic, cq.oc, cq.k, cq.stride, cq.pad = ic, oc, k, st, p
             cq.w, cq.alpha, cq.beta = q.ctypes.data, a.ctypes.data, bt.ctypes.data
