@@ -33,7 +33,9 @@ ABI_SYMBOLS = [
     "dlq_create", "dlq_destroy", "dlq_last_error_string", "dlq_sync", "dlq_stream", "dlq_set_stream", "dlq_version",
     "dlq_quantize_f32_i8", "dlq_dequantize_i8_f32", "dlq_dequantize_i8_f32_per_channel",
     "dlq_conv_weights_pack", "dlq_conv_weights_pack_i8", "dlq_conv_weights_free", "dlq_conv2d_i8", "dlq_fold_bn",
-    "dlq_res_mul",
+    "dlq_res_mul", "dlq_act_bytes", "dlq_conv_required_pad_rows", "dlq_conv2d_i8_act", "dlq_act_from_nchw_i8",
+    "dlq_act_to_nchw_i8", "dlq_stem_pack_input_i8", "dlq_conv_plan_create", "dlq_conv_plan_launch",
+    "dlq_conv_plan_destroy",
     "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
     "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
     "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
@@ -51,6 +53,10 @@ class DlqError(RuntimeError):
 class _Epilogue(C.Structure):
     _fields_ = [("alpha", C.c_void_p), ("beta", C.c_void_p), ("residual", C.c_void_p), ("res_mul", C.c_float),
                 ("relu", C.c_int)]
+
+
+class _Act(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int), ("PR", C.c_int)]
 
 
 class _ResNet18Weights(C.Structure):
@@ -89,6 +95,16 @@ def load_library() -> C.CDLL:
         "dlq_conv2d_i8": (i, [vp, vp, i, i, i, i, vp, C.POINTER(_Epilogue), vp, vp, C.POINTER(i), C.POINTER(i)]),
         "dlq_fold_bn": (None, [vp, vp, vp, vp, f, vp, f, f, i, vp, vp]),
         "dlq_res_mul": (f, [f, f]),
+        "dlq_act_bytes": (sz, [i, i, i, i, i]),
+        "dlq_conv_required_pad_rows": (i, [vp]),
+        "dlq_conv2d_i8_act": (i, [vp, C.POINTER(_Act), vp, C.POINTER(_Epilogue), C.POINTER(_Act), C.POINTER(_Act), vp]),
+        "dlq_conv_plan_create": (i, [vp, C.POINTER(_Act), vp, C.POINTER(_Epilogue), C.POINTER(_Act), C.POINTER(_Act), vp,
+                                     C.POINTER(vp)]),
+        "dlq_conv_plan_launch": (i, [vp, vp]),
+        "dlq_conv_plan_destroy": (None, [vp]),
+        "dlq_act_from_nchw_i8": (i, [vp, vp, C.POINTER(_Act)]),
+        "dlq_act_to_nchw_i8": (i, [vp, C.POINTER(_Act), vp]),
+        "dlq_stem_pack_input_i8": (i, [vp, vp, i, i, i, C.POINTER(_Act)]),
         "dlq_bn_inference_f32": (i, [vp, vp, vp, vp, vp, vp, f, i, i, i, i]),
         "dlq_relu_forward_f32": (i, [vp, vp, sz]),
         "dlq_relu_forward_i8": (i, [vp, vp, sz]),
@@ -233,6 +249,49 @@ class Context:
                                         C.byref(ep) if alpha is not None else None, _ptr(y), _ptr(acc_out),
                                         C.byref(oh), C.byref(ow)))
         return oh.value, ow.value
+
+    # ---- native layout (row-padded NHWC) entry points
+    def new_act(self, n, h, w, c, pr):
+        """allocate a zero-filled row-padded NHWC int8 tensor; returns (torch buffer, _Act)"""
+        import torch
+        nbytes = self.lib.dlq_act_bytes(n, h, w, c, pr)
+        buf = torch.zeros(nbytes + 1024, dtype=torch.int8, device=f"cuda:{self.device}")
+        return buf, _Act(buf.data_ptr(), n, h, w, c, pr)
+
+    def required_pad_rows(self, w: ConvWeights) -> int:
+        return self.lib.dlq_conv_required_pad_rows(w.handle)
+
+    def conv2d_i8_act(self, x_act, w: ConvWeights, y_act=None, alpha=None, beta=None, residual_act=None,
+                      res_mul: float = 0.0, relu: bool = False, acc_out=None):
+        ep = _Epilogue(_ptr(alpha), _ptr(beta), None, res_mul, int(relu))
+        self._ck(self.lib.dlq_conv2d_i8_act(self.h, C.byref(x_act), w.handle, C.byref(ep) if alpha is not None else None,
+                                            C.byref(residual_act) if residual_act is not None else None,
+                                            C.byref(y_act) if y_act is not None else None, _ptr(acc_out)))
+
+    def conv_plan(self, x_act, w: ConvWeights, y_act=None, alpha=None, beta=None, residual_act=None,
+                  res_mul: float = 0.0, relu: bool = False, acc_out=None):
+        """plan once; returns a callable that enqueues the conv (no host planning per launch)"""
+        ep = _Epilogue(_ptr(alpha), _ptr(beta), None, res_mul, int(relu))
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_conv_plan_create(self.h, C.byref(x_act), w.handle, C.byref(ep) if alpha is not None else None,
+                                               C.byref(residual_act) if residual_act is not None else None,
+                                               C.byref(y_act) if y_act is not None else None, _ptr(acc_out), C.byref(h)))
+
+        def launch():
+            self._ck(self.lib.dlq_conv_plan_launch(self.h, h))
+        launch.handle = h
+        launch.destroy = lambda: self.lib.dlq_conv_plan_destroy(h)
+        return launch
+
+    def act_from_nchw_i8(self, x, act):
+        self._ck(self.lib.dlq_act_from_nchw_i8(self.h, _ptr(x), C.byref(act)))
+
+    def act_to_nchw_i8(self, act, y):
+        self._ck(self.lib.dlq_act_to_nchw_i8(self.h, C.byref(act), _ptr(y)))
+
+    def stem_pack_input_i8(self, x, act):
+        n, c, hh, ww = x.shape
+        self._ck(self.lib.dlq_stem_pack_input_i8(self.h, _ptr(x), n, hh, ww, C.byref(act)))
 
     # ---- element-wise / pooling
     def bn_inference_f32(self, x, g, b, m, v, eps: float = 1e-5):

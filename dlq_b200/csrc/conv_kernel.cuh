@@ -55,6 +55,10 @@ struct ConvKernelParams {
   int n_steps;
   uint16_t step_a16[kMaxSteps];   // A view offset of each step inside its sub-patch, in 16-byte units (tap shift * ROWB / 16)
   int a_stages, b_stages, acc_stages;
+  int b_resident;         // 1: all weight steps stay in smem (b_stages == n_steps), loaded once per CTA
+  int cluster;            // CTAs per cluster along grid.x (1, 2 or 4): weight steps are fetched once per cluster
+                          // (each CTA loads 1/cluster of a step and multicasts it)
+  int trips;              // super-tiles per CTA (uniform; trailing ones may be past num_super = all-garbage)
   uint32_t step_bytes;    // weight image bytes per step (n_tile * ROWB, or n_tile*32 for the stem)
   const uint8_t* wimg;    // [n_tiles][n_steps][step_bytes] pre-swizzled smem images
   // epilogue:  y = clamp(rne(fmaf(r, res_mul, fmaf(acc, alpha[oc], beta[oc]))), lo, 127)
@@ -67,6 +71,7 @@ struct ConvKernelParams {
   int8_t* out;            // row-padded NHWC int8
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
+  int dbg;                // tuning experiments only: 1 = skip TMEM loads, 2 = skip MMA issue, 4 = skip A loads
 };
 
 __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
@@ -92,7 +97,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align to 1024 B with pointer arithmetic on the __shared__ array (keeps the address space visible to
+  // the compiler so alpha/beta reads become LDS, not generic loads)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t a_stage_bytes = static_cast<uint32_t>(p.sub_bytes);
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   uint8_t* sA = smem;
@@ -118,7 +125,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.cluster); }
     for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], n_epi_warps); }
     fence_mbar_init();
     tma_prefetch_desc(&tm0);
@@ -133,21 +140,27 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int super_pos = p.MT * kTileM;
+  const int st_end = static_cast<int>(blockIdx.x) + p.trips * static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
     if (elect_one()) {
       uint32_t as = 0, aph = 0;
-      for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
+      for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
         const int v0 = (st * super_pos) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
           mbar_wait(&a_empty[as], aph ^ 1u);
-          mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
-          tma_load_3d(sA + static_cast<size_t>(as) * a_stage_bytes, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
-                      p.row_mul * v0 + p.sub_row_off[s]);
+          if (p.dbg & 4) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
+            tma_load_3d(sA + static_cast<size_t>(as) * a_stage_bytes, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
+                        p.row_mul * v0 + p.sub_row_off[s]);
+          }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }
       }
@@ -157,12 +170,21 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     if (elect_one()) {
       uint32_t bs = 0, bph = 0;
       const uint8_t* wsrc = p.wimg + static_cast<size_t>(n_blk) * p.n_steps * p.step_bytes;
-      for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
+      for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
+        if (p.b_resident && st != static_cast<int>(blockIdx.x)) break;   // resident weights: loaded once
         for (int k = 0; k < p.n_steps; ++k) {
           mbar_wait(&b_empty[bs], bph ^ 1u);
           mbar_expect_tx(&b_full[bs], p.step_bytes);
-          bulk_g2s(sB + static_cast<size_t>(bs) * b_stage_bytes, wsrc + static_cast<size_t>(k) * p.step_bytes,
-                   p.step_bytes, &b_full[bs]);
+          if (p.cluster > 1) {
+            const uint32_t slice = p.step_bytes / static_cast<uint32_t>(p.cluster);
+            const uint32_t off = cluster_ctarank() * slice;
+            bulk_g2s_multicast(sB + static_cast<size_t>(bs) * b_stage_bytes + off,
+                               wsrc + static_cast<size_t>(k) * p.step_bytes + off, slice, &b_full[bs],
+                               static_cast<uint16_t>((1u << p.cluster) - 1u));
+          } else {
+            bulk_g2s(sB + static_cast<size_t>(bs) * b_stage_bytes, wsrc + static_cast<size_t>(k) * p.step_bytes,
+                     p.step_bytes, &b_full[bs]);
+          }
           if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
         }
       }
@@ -179,7 +201,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     const uint32_t b_lo_flags =
         static_cast<uint32_t>(umma_smem_desc(0, ROWB == 16 ? static_cast<uint32_t>(p.n_tile) * 16u : 0u, B_SBO, LAYOUT));
     uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
-    for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
+    for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
       const int g0 = st * super_pos;
       const int v0 = g0 / p.Wp;
       const uint32_t in_patch16 = static_cast<uint32_t>(g0 - v0 * p.Wp) * (ROWB / 16);   // first position's offset
@@ -192,9 +214,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
             a_lo_flags + (smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) >> 4) + in_patch16;
         const int k_end = p.sub_step0[s + 1];
         for (int k = p.sub_step0[s]; k < k_end; ++k) {
-          mbar_wait(&b_full[bs], bph);
+          mbar_wait(&b_full[bs], p.b_resident ? 0u : bph);
           tc_fence_after();
-          if (leader) {
+          if (leader && !(p.dbg & 2)) {
             const uint32_t b_lo = b_lo_flags + (smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes) >> 4);
             uint32_t a_lo = a_lo_base + p.step_a16[k];
             uint32_t d = d_base;
@@ -208,7 +230,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
               a_lo += TILE16;
               d += static_cast<uint32_t>(p.n_tile);
             }
-            umma_commit(&b_empty[bs]);   // weight stage free once these MMAs retire
+            if (!p.b_resident) {   // weight stage free (in every CTA of the cluster) once these MMAs retire
+              if (p.cluster > 1) umma_commit_multicast(&b_empty[bs], static_cast<uint16_t>((1u << p.cluster) - 1u));
+              else umma_commit(&b_empty[bs]);
+            }
+          }
+          if (leader && (p.dbg & 2) && !p.b_resident) {
+            if (p.cluster > 1) umma_commit_multicast(&b_empty[bs], static_cast<uint16_t>((1u << p.cluster) - 1u));
+            else umma_commit(&b_empty[bs]);
           }
           __syncwarp();
           if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
@@ -235,10 +264,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     const uint32_t relu_floor = p.relu ? 0u : 0x80808080u;   // per-byte signed max with 0 (ReLU) or -128 (no-op)
     const float res_mul = p.res_mul;
     uint32_t cs = 0, cph = 0;
-    for (int st = blockIdx.x; st < p.num_super; st += gridDim.x) {
+    for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
       mbar_wait(&acc_full[cs], cph);
       tc_fence_after();
-      for (int mt = 0; mt < p.MT; ++mt) {
+      for (int mt = 0; mt < ((p.dbg & 1) ? 0 : p.MT); ++mt) {
         const int g = st * super_pos + mt * kTileM + row;
         const int vrow = g / p.Wp, x = g - vrow * p.Wp;
         const int n = vrow / p.Pv, r = vrow - n * p.Pv;
@@ -303,6 +332,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();   // nobody leaves while a peer may still write its smem / barriers
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 

@@ -6,6 +6,7 @@
 // plan-once / launch-many split.
 #include "dlq_internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dlq {
 
@@ -132,7 +133,9 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
       DLQ_ARG(ctx, false, "unsupported (kernel, stride, pad) combination");
     }
   }
-  out->n_tile = (OC % 128 == 0) ? 128 : 64;
+  // tcgen05.mma (SS, M=128, K=32) costs ~42 + N/2 cycles (probe/mma_rate.cu): the widest N amortises the A fetch
+  out->n_tile = (OC % 256 == 0) ? 256 : (OC % 128 == 0) ? 128 : 64;
+  if (const char* e = getenv("DLQ_DBG_NTILE")) { const int v = atoi(e); if (v >= 64 && OC % v == 0) out->n_tile = v; }
   std::vector<SubDesc> subs;
   std::vector<StepDesc> steps;
   make_schedule(out, subs, steps);
@@ -249,19 +252,33 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 2048 /*alpha,beta,barriers*/;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
+  if (const char* e = getenv("DLQ_DBG_MT")) MT = std::max(1, atoi(e));
   int NR = 0;
+  const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;
   for (;; MT >>= 1) {
     NR = (p.Wp - 1 + MT * kTileM - 1 + maxshift) / p.Wp + 1;
     p.tma_bytes = NR * p.Wp * rowb;
     p.sub_bytes = (p.tma_bytes + 1023) & ~1023;
-    p.b_stages = std::min(p.n_steps, 4);
-    const size_t b_bytes = static_cast<size_t>(p.b_stages) * b_stage_bytes;
-    const int want_a = std::min(4, p.n_sub + 1);
+    // weights resident in smem when they are small (stem, layer1, stride-2 / 1x1 convs): no per-tile re-fetch
+    p.b_resident = (all_b <= 80 * 1024 && all_b + 2 * static_cast<size_t>(p.sub_bytes) <= budget) ? 1 : 0;
+    const int min_a = 2;
+    if (p.b_resident) {
+      p.b_stages = p.n_steps;
+    } else {
+      const size_t left = budget > static_cast<size_t>(min_a) * p.sub_bytes ? budget - static_cast<size_t>(min_a) * p.sub_bytes : 0;
+      p.b_stages = static_cast<int>(std::min<size_t>(std::min(p.n_steps, 8), left / b_stage_bytes));
+    }
+    const size_t b_bytes = static_cast<size_t>(std::max(p.b_stages, 0)) * b_stage_bytes;
+    const int want_a = std::min(4, p.n_sub + 2);
     const int fit_a = budget > b_bytes ? static_cast<int>((budget - b_bytes) / p.sub_bytes) : 0;
     p.a_stages = std::min(want_a, fit_a);
-    if ((p.a_stages >= 2 && es * NR <= 256) || MT == 1) break;
+    if ((p.a_stages >= 2 && p.b_stages >= std::min(p.n_steps, 3) && es * NR <= 256) || MT == 1) break;
   }
-  DLQ_ARG(ctx, p.a_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256, "conv patch does not fit shared memory / TMA box");
+  // debug / tuning overrides (environment; not used by tests or the benchmark)
+  if (const char* e = getenv("DLQ_DBG_A_STAGES")) p.a_stages = atoi(e);
+  if (const char* e = getenv("DLQ_DBG_B_STAGES")) { if (!p.b_resident) p.b_stages = atoi(e); }
+  DLQ_ARG(ctx, p.a_stages >= 1 && p.b_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256,
+          "conv patch does not fit shared memory / TMA box");
   p.MT = MT;
   p.acc_stages = (2 * MT * p.n_tile <= 512) ? 2 : 1;
   const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
@@ -277,6 +294,8 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.out = out.ptr;
   p.out_PR = out.PR;
   p.acc_out = acc_out;
+  if (getenv("DLQ_DBG_NO_STORE")) { p.out = nullptr; p.acc_out = nullptr; }
+  if (const char* e = getenv("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
 
   // ---- TMA descriptor over the row-padded NHWC input: dims (C bytes, W, rows)
   EncodeTiledFn enc = encode_tiled_fn();
@@ -302,8 +321,20 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   }
 
   const int n_tiles = w->OC / w->n_tile;
-  L->grid = dim3(static_cast<unsigned>(std::min(p.num_super, std::max(1, ctx->num_sms / n_tiles))),
-                 static_cast<unsigned>(n_tiles), 1);
+  int gx = std::min(p.num_super, std::max(1, ctx->num_sms / n_tiles));
+  // streamed weights: CTAs of a cluster share every weight step through multicast (L2 -> SM traffic / cluster)
+  p.cluster = 1;
+  if (!p.b_resident) {
+    // measured on B200 (profiles/r01_mma_rate.log, r01_cluster_sweep.txt): the convs are bound by the MMA
+    // operand fetch, not by L2 -> SM weight traffic, so sharing buys nothing yet; off unless requested
+    int want = 1;
+    if (const char* e = getenv("DLQ_DBG_CLUSTER")) want = std::max(1, atoi(e));
+    while (want > 1 && (gx < want || (p.step_bytes / want) % 16 != 0)) want >>= 1;
+    p.cluster = want;
+    gx = gx / p.cluster * p.cluster;
+  }
+  p.trips = (p.num_super + gx - 1) / gx;
+  L->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_tiles), 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
             2 * sizeof(float) * p.n_tile + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
@@ -318,8 +349,19 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
                                        static_cast<int>(ctx->smem_optin)));
     configured[ctx->device & 15] = ctx->smem_optin;
   }
-  conv_i8_kernel<ROWB><<<L.grid, L.block, L.smem, ctx->stream>>>(L.tmap, L.p);
-  DLQ_CUDA(ctx, cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = L.grid;
+  cfg.blockDim = L.block;
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(L.p.cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB>, L.tmap, L.p));
   return DLQ_OK;
 }
 

@@ -244,6 +244,87 @@ int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, con
 
 }  // extern "C"
 
+struct dlq_conv_plan {
+  ConvLaunch L;
+};
+
+extern "C" {
+
+size_t dlq_act_bytes(int N, int H, int W, int C, int PR) {
+  return static_cast<size_t>(PR + static_cast<size_t>(N) * (H + PR)) * W * C;
+}
+int dlq_conv_required_pad_rows(const dlq_conv_weights* w) { return w ? conv_required_in_pr(w) : 0; }
+
+static Act to_act(const dlq_act* a) {
+  Act r;
+  r.ptr = a->ptr; r.N = a->N; r.H = a->H; r.W = a->W; r.C = a->C; r.PR = a->PR;
+  return r;
+}
+
+static int plan_act(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, const dlq_epilogue* ep,
+                    const dlq_act* residual, const dlq_act* y, int32_t* acc_out, ConvLaunch* L) {
+  DLQ_ARG(ctx, x && x->ptr && w && (y || acc_out), "null pointer");
+  DLQ_ARG(ctx, !(y && y->ptr) || (ep && ep->alpha && ep->beta), "an int8 output needs an epilogue with alpha and beta");
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  Act in = to_act(x), out, res;
+  if (y) {
+    out = to_act(y);
+  } else {
+    out.N = in.N; out.C = w->OC; out.PR = 0;
+    if (w->kind == CONV_STEM) { out.H = in.H; out.W = in.W; }
+    else conv_out_dims(w, in.H, in.W, &out.H, &out.W);
+  }
+  if (residual) res = to_act(residual);
+  return plan_conv(ctx, w, in, out, ep ? ep->alpha : nullptr, ep ? ep->beta : nullptr, residual ? &res : nullptr,
+                   ep ? ep->res_mul : 0.f, ep ? ep->relu : 0, acc_out, L);
+}
+
+int dlq_conv2d_i8_act(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, const dlq_epilogue* ep,
+                      const dlq_act* residual, const dlq_act* y, int32_t* acc_out) {
+  if (!ctx) return DLQ_ERR_ARG;
+  if (x && x->N == 0) return DLQ_OK;
+  ConvLaunch L;
+  const int rc = plan_act(ctx, x, w, ep, residual, y, acc_out, &L);
+  if (rc != DLQ_OK) return rc;
+  return launch_conv(ctx, L);
+}
+
+int dlq_conv_plan_create(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, const dlq_epilogue* ep,
+                         const dlq_act* residual, const dlq_act* y, int32_t* acc_out, dlq_conv_plan** out) {
+  if (!ctx || !out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  DLQ_ARG(ctx, x && x->N > 0, "empty batch");
+  std::unique_ptr<dlq_conv_plan> P(new dlq_conv_plan());
+  const int rc = plan_act(ctx, x, w, ep, residual, y, acc_out, &P->L);
+  if (rc != DLQ_OK) return rc;
+  *out = P.release();
+  return DLQ_OK;
+}
+int dlq_conv_plan_launch(dlq_ctx* ctx, const dlq_conv_plan* plan) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, plan != nullptr, "null plan");
+  return launch_conv(ctx, plan->L);
+}
+void dlq_conv_plan_destroy(dlq_conv_plan* plan) { delete plan; }
+
+int dlq_act_from_nchw_i8(dlq_ctx* ctx, const int8_t* x, const dlq_act* a) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && a && a->ptr, "null pointer");
+  return nchw_to_act_i8(ctx, x, to_act(a));
+}
+int dlq_act_to_nchw_i8(dlq_ctx* ctx, const dlq_act* a, int8_t* y) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, y && a && a->ptr, "null pointer");
+  return act_to_nchw_i8(ctx, to_act(a), y);
+}
+int dlq_stem_pack_input_i8(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const dlq_act* a) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, x && a && a->ptr, "null pointer");
+  return nchw_i8_to_stem_s2d(ctx, x, N, H, W, to_act(a));
+}
+
+}  // extern "C"
+
 // ================================================================================================
 // ResNet-18 runner
 // ================================================================================================

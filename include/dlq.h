@@ -94,6 +94,31 @@ float dlq_res_mul(float s_r, float s_y);
 int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
                   const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW);
 
+/* Native-layout variant (no NCHW transposes): activations as the library keeps them internally —
+ * row-padded NHWC int8:  [PR zero rows][image 0: H rows of W*C bytes][PR zero rows][image 1] ...
+ * The zero rows are the vertical padding; the caller zero-fills the buffer once (dlq_act_bytes) and the
+ * kernels never write them.  x->PR must be >= dlq_conv_required_pad_rows(w); for stride-2 convs H+PR must be
+ * even; the 3-channel stem takes the 2x2 space-to-depth image (H/2 x W/2 x 16 B, see dlq_stem_pack_input_i8). */
+typedef struct {
+  int8_t* ptr; /* device */
+  int N, H, W, C, PR;
+} dlq_act;
+size_t dlq_act_bytes(int N, int H, int W, int C, int PR);
+int dlq_conv_required_pad_rows(const dlq_conv_weights* w);
+/* residual (may be NULL) shares y's geometry except PR; acc_out: dense NHWC int32 [N,OH,OW,OC] or NULL */
+int dlq_conv2d_i8_act(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, const dlq_epilogue* ep,
+                      const dlq_act* residual, const dlq_act* y, int32_t* acc_out);
+/* plan-once / launch-many form of the same call (no host planning or descriptor encoding on the hot path) */
+typedef struct dlq_conv_plan dlq_conv_plan;
+int dlq_conv_plan_create(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, const dlq_epilogue* ep,
+                         const dlq_act* residual, const dlq_act* y, int32_t* acc_out, dlq_conv_plan** out);
+int dlq_conv_plan_launch(dlq_ctx* ctx, const dlq_conv_plan* plan);
+void dlq_conv_plan_destroy(dlq_conv_plan* plan);
+/* layout helpers: dense NCHW int8 <-> row-padded NHWC; [N,3,H,W] int8 -> stem space-to-depth */
+int dlq_act_from_nchw_i8(dlq_ctx* ctx, const int8_t* x_nchw, const dlq_act* a);
+int dlq_act_to_nchw_i8(dlq_ctx* ctx, const dlq_act* a, int8_t* y_nchw);
+int dlq_stem_pack_input_i8(dlq_ctx* ctx, const int8_t* x_nchw, int N, int H, int W, const dlq_act* a);
+
 /* ------------------------------------------------------------------ element-wise / pooling (standalone,
  * kept for per-layer API parity; the fused network path does not launch them) */
 /* K/bn_inference.cu:6-28 — in place, y = g*((x-m)/sqrtf(v+eps)) + b, c = (idx/(OH*OW)) % C */
