@@ -33,6 +33,8 @@ namespace dlq {
 constexpr int kMaxSteps = 40;    // K steps (tap x channel-block) per conv
 constexpr int kMaxPlanes = 4;
 constexpr int kTileM = 128;
+constexpr int kEpiStageRow = 80;                       // bytes per staged row (64 B payload + pad: conflict-free STS.128)
+constexpr int kEpiStageBytes = 32 * kEpiStageRow;      // per epilogue warp
 
 struct ConvKernelParams {
   // virtual output space
@@ -72,6 +74,7 @@ struct ConvKernelParams {
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
   int dbg;                // tuning experiments only: 1 = skip TMEM loads, 2 = skip MMA issue, 4 = skip A loads
+  long long* dbg_times;   // optional [gridDim.x*gridDim.y][8] cycle counters (tuning): see conv_plan.cu
 };
 
 __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
@@ -84,7 +87,7 @@ __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
 
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha,beta: 2*n_tile f32]
-//   [barriers][tmem slot]
+//   [epilogue staging: 8 * kEpiStageBytes][barriers][tmem slot]
 template <int ROWB>
 __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p) {
@@ -106,7 +109,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   uint8_t* sB = sA + static_cast<size_t>(p.a_stages) * a_stage_bytes;
   float* s_alpha = reinterpret_cast<float*>(sB + static_cast<size_t>(p.b_stages) * b_stage_bytes);
   float* s_beta = s_alpha + p.n_tile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_beta + p.n_tile);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.n_tile);          // [epilogue warps][kEpiStageBytes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 8 * kEpiStageBytes);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_stages;
   uint64_t* b_full = a_empty + p.a_stages;
@@ -150,10 +154,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     // ===================================================================== A (activation patch) producer
     if (elect_one()) {
       uint32_t as = 0, aph = 0;
+      long long t_wait = 0;
+      const long long t_begin = clock64();
       for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
         const int v0 = (st * super_pos) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
+          const long long tw = clock64();
           mbar_wait(&a_empty[as], aph ^ 1u);
+          t_wait += clock64() - tw;
           if (p.dbg & 4) {
             mbar_arrive(&a_full[as]);
           } else {
@@ -163,6 +171,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }
+      }
+      if (p.dbg_times) {
+        long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+        d[6] = clock64() - t_begin; d[7] = t_wait;
       }
     }
   } else if (warp == 2) {
@@ -201,20 +213,28 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     const uint32_t b_lo_flags =
         static_cast<uint32_t>(umma_smem_desc(0, ROWB == 16 ? static_cast<uint32_t>(p.n_tile) * 16u : 0u, B_SBO, LAYOUT));
     uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+    long long t_acc = 0, t_a = 0, t_b = 0;
+    const long long t_begin = clock64();
     for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
       const int g0 = st * super_pos;
       const int v0 = g0 / p.Wp;
       const uint32_t in_patch16 = static_cast<uint32_t>(g0 - v0 * p.Wp) * (ROWB / 16);   // first position's offset
+      long long tw = clock64();
       mbar_wait(&acc_empty[cs], cph ^ 1u);
+      t_acc += clock64() - tw;
       const uint32_t d_base = tmem_base + cs * acc_cols;
       for (int s = 0; s < p.n_sub; ++s) {
+        tw = clock64();
         mbar_wait(&a_full[as], aph);
+        t_a += clock64() - tw;
         tc_fence_after();
         const uint32_t a_lo_base =
             a_lo_flags + (smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) >> 4) + in_patch16;
         const int k_end = p.sub_step0[s + 1];
         for (int k = p.sub_step0[s]; k < k_end; ++k) {
+          tw = clock64();
           mbar_wait(&b_full[bs], p.b_resident ? 0u : bph);
+          t_b += clock64() - tw;
           tc_fence_after();
           if (leader && !(p.dbg & 2)) {
             const uint32_t b_lo = b_lo_flags + (smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes) >> 4);
@@ -250,84 +270,128 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
       __syncwarp();
       if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
+    if (p.dbg_times && leader) {
+      long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+      d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_b;
+    }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
+    // Work unit: (M tile, 64-column block); the two warp groups take alternate units, the four warps of a
+    // group own the four TMEM lane quarters.  Per unit a warp turns 32 rows x 64 int32 accumulators into
+    // 32 x 64 int8.  Global traffic goes through a per-warp smem staging tile so that every LDG/STG
+    // instruction covers whole 64-byte pixel rows (8 rows x 64 B per instruction) instead of 32 scattered
+    // 16-byte pieces: residual rows are loaded coalesced -> staged -> read back row-per-lane; results are
+    // staged row-per-lane -> read back coalesced -> stored.
     const int ew = warp - 4;
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int n_groups = n_epi_warps >> 2;              // 1 or 2 column groups
-    const int grp = (ew >> 2);                          // which column group this warp handles
-    const int cols_per_grp = p.n_tile / n_groups;       // multiple of 32
-    const int col_lo = grp * cols_per_grp;
+    const int n_groups = n_epi_warps >> 2;
+    const int grp = ew >> 2;
     const int row = quarter * 32 + lane;                // accumulator row within the tile
     const bool has_res = p.residual != nullptr;
     const int out_pitch = p.Ho + p.out_PR, res_pitch = p.Ho + p.res_PR;
     const uint32_t relu_floor = p.relu ? 0u : 0x80808080u;   // per-byte signed max with 0 (ReLU) or -128 (no-op)
     const float res_mul = p.res_mul;
+    const int cblocks = p.n_tile >> 6;
+    const int n_units = p.MT * cblocks;
+    uint8_t* stage = s_stage + ew * kEpiStageBytes;     // [32 rows][kEpiStageRow bytes]
+    uint8_t* my_row = stage + lane * kEpiStageRow;
+    const int crow = lane >> 2, cq = lane & 3;          // coalesced phase: row within a group of 8, 16-byte quarter
+    constexpr uint32_t kInvalid = 0xFFFFFFFFu;
     uint32_t cs = 0, cph = 0;
+    long long t_wait = 0;
+    const long long t_begin = clock64();
     for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
+      const long long tw = clock64();
       mbar_wait(&acc_full[cs], cph);
+      t_wait += clock64() - tw;
       tc_fence_after();
-      for (int mt = 0; mt < ((p.dbg & 1) ? 0 : p.MT); ++mt) {
+      for (int unit = (p.dbg & 1) ? n_units : grp; unit < n_units; unit += n_groups) {
+        const int mt = unit / cblocks, c0 = (unit - mt * cblocks) << 6;
         const int g = st * super_pos + mt * kTileM + row;
         const int vrow = g / p.Wp, x = g - vrow * p.Wp;
         const int n = vrow / p.Pv, r = vrow - n * p.Pv;
         const bool valid = (x < p.Wo) && (r < p.Ho) && (n < p.N);
-        const size_t opix = (static_cast<size_t>(p.out_PR + n * out_pitch + r) * p.Wo + x);
-        const size_t rpix = (static_cast<size_t>(p.res_PR + n * res_pitch + r) * p.Wo + x);
-        const uint32_t taddr = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile +
+        const uint32_t opix = valid ? static_cast<uint32_t>((p.out_PR + n * out_pitch + r) * p.Wo + x) : kInvalid;
+        const uint32_t rpix = valid ? static_cast<uint32_t>((p.res_PR + n * res_pitch + r) * p.Wo + x) : kInvalid;
+        const uint32_t taddr = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile + c0 +
                                (static_cast<uint32_t>(quarter * 32) << 16);
-        for (int c = col_lo; c < col_lo + cols_per_grp; c += 32) {
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int srow = 8 * j + crow;
+            const uint32_t rp = __shfl_sync(0xffffffffu, rpix, srow);
+            int4 v = make_int4(0, 0, 0, 0);
+            if (rp != kInvalid)
+              v = __ldg(reinterpret_cast<const int4*>(p.residual + static_cast<size_t>(rp) * p.OC + n0 + c0) + cq);
+            *reinterpret_cast<int4*>(stage + srow * kEpiStageRow + cq * 16) = v;
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_32x32b_x32(taddr + h * 32, v);
           int4 rv[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
-          if (has_res && valid) {
-            const int4* rp = reinterpret_cast<const int4*>(p.residual + rpix * p.OC + n0 + c);
-            rv[0] = __ldg(rp);
-            rv[1] = __ldg(rp + 1);
+          if (has_res) {
+            rv[0] = *reinterpret_cast<const int4*>(my_row + h * 32);
+            rv[1] = *reinterpret_cast<const int4*>(my_row + h * 32 + 16);
           }
           tmem_ld_wait();
-          if (valid) {
-            if (p.acc_out) {
-              const size_t dpix = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
-              int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix * p.OC + n0 + c);
+          if (p.acc_out && valid) {
+            const size_t dpix = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
+            int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix * p.OC + n0 + c0 + h * 32);
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                dst[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
+          }
+          const float4* a4 = reinterpret_cast<const float4*>(s_alpha + c0 + h * 32);
+          const float4* b4 = reinterpret_cast<const float4*>(s_beta + c0 + h * 32);
+          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
+          uint32_t packed[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 al = a4[j], be = b4[j];
+            float t0 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 0])), al.x, be.x);
+            float t1 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 1])), al.y, be.y);
+            float t2 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 2])), al.z, be.z);
+            float t3 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 3])), al.w, be.w);
+            if (has_res) {
+              const uint32_t w = rw[j];
+              t0 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w)), res_mul, t0);
+              t1 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 8)), res_mul, t1);
+              t2 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 16)), res_mul, t2);
+              t3 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 24)), res_mul, t3);
             }
-            if (p.out) {
-              const float4* a4 = reinterpret_cast<const float4*>(s_alpha + c);
-              const float4* b4 = reinterpret_cast<const float4*>(s_beta + c);
-              const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-              uint32_t packed[8];
+            const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2),
+                                             __float2int_rn(t3));
+            packed[j] = __vmaxs4(q, relu_floor);
+          }
+          *reinterpret_cast<int4*>(my_row + h * 32) = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
+          *reinterpret_cast<int4*>(my_row + h * 32 + 16) =
+              make_int4((int)packed[4], (int)packed[5], (int)packed[6], (int)packed[7]);
+        }
+        __syncwarp();
+        if (p.out) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 al = a4[j], be = b4[j];
-                float t0 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 0])), al.x, be.x);
-                float t1 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 1])), al.y, be.y);
-                float t2 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 2])), al.z, be.z);
-                float t3 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 3])), al.w, be.w);
-                if (has_res) {
-                  const uint32_t w = rw[j];
-                  t0 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w)), res_mul, t0);
-                  t1 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 8)), res_mul, t1);
-                  t2 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 16)), res_mul, t2);
-                  t3 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 24)), res_mul, t3);
-                }
-                const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2),
-                                                 __float2int_rn(t3));
-                packed[j] = __vmaxs4(q, relu_floor);
-              }
-              int4* dst = reinterpret_cast<int4*>(p.out + opix * p.OC + n0 + c);
-              dst[0] = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
-              dst[1] = make_int4((int)packed[4], (int)packed[5], (int)packed[6], (int)packed[7]);
+          for (int j = 0; j < 4; ++j) {
+            const int srow = 8 * j + crow;
+            const uint32_t op = __shfl_sync(0xffffffffu, opix, srow);
+            if (op != kInvalid) {
+              const int4 v = *reinterpret_cast<const int4*>(stage + srow * kEpiStageRow + cq * 16);
+              *(reinterpret_cast<int4*>(p.out + static_cast<size_t>(op) * p.OC + n0 + c0) + cq) = v;
             }
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[cs]);
       if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
+    }
+    if (p.dbg_times && ew == 0 && lane == 0) {
+      long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+      d[4] = clock64() - t_begin; d[5] = t_wait;
     }
   }
   tc_fence_before();

@@ -249,7 +249,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   }
 
   // ---- tile shape: MT tiles of 128 positions per super-tile, two TMEM accumulator stages when they fit
-  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 2048 /*alpha,beta,barriers*/;
+  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 3072 /*alpha,beta,barriers*/ - 8 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
   if (const char* e = getenv("DLQ_DBG_MT")) MT = std::max(1, atoi(e));
@@ -296,6 +296,14 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.acc_out = acc_out;
   if (getenv("DLQ_DBG_NO_STORE")) { p.out = nullptr; p.acc_out = nullptr; }
   if (const char* e = getenv("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
+  // DLQ_DBG_TIMES=1: per-CTA cycle counters (MMA warp: total / wait acc_empty / wait a_full / wait b_full;
+  // epilogue warp 0: total / wait acc_full; A producer: total / wait a_empty), printed by launch_conv
+  if (getenv("DLQ_DBG_TIMES")) {
+    static long long* buf = nullptr;
+    if (!buf) cudaMalloc(&buf, 8 * sizeof(long long) * 1024);
+    cudaMemset(buf, 0, 8 * sizeof(long long) * 1024);
+    p.dbg_times = buf;
+  }
 
   // ---- TMA descriptor over the row-padded NHWC input: dims (C bytes, W, rows)
   EncodeTiledFn enc = encode_tiled_fn();
@@ -337,7 +345,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   L->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_tiles), 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
-            2 * sizeof(float) * p.n_tile + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
+            2 * sizeof(float) * p.n_tile + 8 * kEpiStageBytes + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
   return DLQ_OK;
 }
 
@@ -362,6 +370,18 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB>, L.tmap, L.p));
+  if (L.p.dbg_times) {
+    cudaStreamSynchronize(ctx->stream);
+    const int nb = static_cast<int>(L.grid.x * L.grid.y);
+    std::vector<long long> h(static_cast<size_t>(nb) * 8);
+    cudaMemcpy(h.data(), L.p.dbg_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    double a[8] = {0};
+    for (int b = 0; b < nb; ++b)
+      for (int j = 0; j < 8; ++j) a[j] += static_cast<double>(h[static_cast<size_t>(b) * 8 + j]) / nb;
+    fprintf(stderr, "[dbg_times] grid %ux%u MT=%d n_tile=%d trips=%d | mma: total %.0f wait_acc %.0f wait_a %.0f wait_b %.0f | "
+                    "epi: total %.0f wait_acc_full %.0f | prodA: total %.0f wait_a_empty %.0f (cycles, mean over CTAs)\n",
+            L.grid.x, L.grid.y, L.p.MT, L.p.n_tile, L.p.trips, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+  }
   return DLQ_OK;
 }
 
