@@ -351,6 +351,9 @@ struct dlq_resnet18 {
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
+  cudaStream_t copy_stream = nullptr;   // forward_host pipelining
+  cudaEvent_t copy_done[64] = {nullptr};
+  cudaEvent_t compute_done = nullptr;
 };
 
 namespace {
@@ -434,6 +437,11 @@ void dlq_resnet18_destroy(dlq_resnet18* m) {
   cudaStreamSynchronize(m->ctx->stream);
   for (void* p : m->allocs) cudaFree(p);
   for (auto& c : m->conv) dlq_conv_weights_free(c);
+  if (m->copy_stream) {
+    cudaStreamDestroy(m->copy_stream);
+    for (auto& e : m->copy_done) if (e) cudaEventDestroy(e);
+    if (m->compute_done) cudaEventDestroy(m->compute_done);
+  }
   delete m;
 }
 
@@ -490,7 +498,11 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     quantize_rows(w->fc_w, 1000, 512, q, s);
     std::vector<float> sc(1000), bias(w->fc_b, w->fc_b + 1000);
     for (int o = 0; o < 1000; ++o) sc[o] = static_cast<float>(static_cast<double>(w->act_scale[kActGap]) * static_cast<double>(s[o]));
-    int rc = upload(m.get(), q, &m->d_fc_w);
+    // transposed image for the fused GAP+FC kernel: [512/16][1024][16 B]
+    std::vector<int8_t> qT(static_cast<size_t>(32) * 1024 * 16, 0);
+    for (int o = 0; o < 1000; ++o)
+      for (int k = 0; k < 512; ++k) qT[(static_cast<size_t>(k / 16) * 1024 + o) * 16 + (k % 16)] = q[static_cast<size_t>(o) * 512 + k];
+    int rc = upload(m.get(), qT, &m->d_fc_w);
     if (rc != DLQ_OK) return rc;
     rc = upload(m.get(), sc, &m->d_fc_scale);
     if (rc != DLQ_OK) return rc;
@@ -623,13 +635,37 @@ int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float
   DLQ_ARG(ctx, x_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
   if (N == 0) return DLQ_OK;
   DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
-  DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_x, x_host, static_cast<size_t>(N) * 3 * 224 * 224 * sizeof(float),
-                                cudaMemcpyHostToDevice, ctx->stream));
-  const int rc = dlq_resnet18_forward(m, m->d_x, N, m->d_logits);
-  if (rc != DLQ_OK) return rc;
+  const size_t img = static_cast<size_t>(3) * 224 * 224;
+  // Large batches are pipelined: the H2D copy of chunk k+1 (copy stream) overlaps the forward of chunk k
+  // (compute stream).  The fp32 input is 602 KB/image, so the host link, not the GPU, bounds this entry point.
+  const int chunk = (N >= 128) ? 64 : N;
+  if (!m->copy_stream) {
+    DLQ_CUDA(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : m->copy_done) DLQ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    DLQ_CUDA(ctx, cudaEventCreateWithFlags(&m->compute_done, cudaEventDisableTiming));
+  }
+  // the copy stream must not overwrite d_x while a previous call's compute still reads it
+  DLQ_CUDA(ctx, cudaEventRecord(m->compute_done, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->compute_done, 0));
+  int k = 0;
+  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
+    const int n = std::min(chunk, N - n0);
+    DLQ_ARG(ctx, k < static_cast<int>(sizeof(m->copy_done) / sizeof(m->copy_done[0])), "too many chunks");
+    DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_x + n0 * img, x_host + n0 * img, n * img * sizeof(float), cudaMemcpyHostToDevice,
+                                  m->copy_stream));
+    DLQ_CUDA(ctx, cudaEventRecord(m->copy_done[k], m->copy_stream));
+  }
+  k = 0;
+  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
+    const int n = std::min(chunk, N - n0);
+    DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copy_done[k], 0));
+    const int rc = forward_impl(m, m->d_x + n0 * img, n, m->d_logits + static_cast<size_t>(n0) * 1000, nullptr);
+    if (rc != DLQ_OK) return rc;
+  }
   DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, m->d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
                                 cudaMemcpyDeviceToHost, ctx->stream));
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->last_N = std::min(chunk, N - (k - 1) * chunk);   // checkpoints refer to the last chunk
   return DLQ_OK;
 }
 

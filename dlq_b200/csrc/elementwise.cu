@@ -218,33 +218,64 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
 // ------------------------------------------------------------------------------------------------
 __global__ void maxpool_act_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int N, int H, int W,
                                    int C, int PRi, int OH, int OW, int PRo) {
+  // one thread = 16 channels of a 2x2 block of output pixels: 5x5 input pixels (25 x 16-byte loads for 4
+  // outputs instead of 36), rows streamed through a horizontal 3-max then combined vertically.
   const int cv = C / 16;
-  const size_t total = static_cast<size_t>(N) * OH * OW * cv;
+  const int OH2 = (OH + 1) / 2, OW2 = (OW + 1) / 2;
+  const size_t total = static_cast<size_t>(N) * OH2 * OW2 * cv;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c16 = static_cast<int>(i % cv);
-    const int ow = static_cast<int>((i / cv) % OW);
-    const int oh = static_cast<int>((i / (static_cast<size_t>(cv) * OW)) % OH);
-    const int n = static_cast<int>(i / (static_cast<size_t>(cv) * OW * OH));
-    uint32_t m[4] = {0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u};
+    const int ow0 = 2 * static_cast<int>((i / cv) % OW2);
+    const int oh0 = 2 * static_cast<int>((i / (static_cast<size_t>(cv) * OW2)) % OH2);
+    const int n = static_cast<int>(i / (static_cast<size_t>(cv) * OW2 * OH2));
+    uint32_t m[2][2][4];
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ih = oh * 2 - 1 + kh;
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[a][b][j] = 0x80808080u;
+    const int ih0 = oh0 * 2 - 1, iw0 = ow0 * 2 - 1;
+#pragma unroll
+    for (int rr = 0; rr < 5; ++rr) {
+      const int ih = ih0 + rr;
       if (ih < 0 || ih >= H) continue;
       const size_t row = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + ih;
+      uint32_t h[2][4];
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ow * 2 - 1 + kw;
+      for (int j = 0; j < 4; ++j) h[0][j] = h[1][j] = 0x80808080u;
+#pragma unroll
+      for (int cc = 0; cc < 5; ++cc) {
+        const int iw = iw0 + cc;
         if (iw < 0 || iw >= W) continue;
         const int4 v = __ldg(reinterpret_cast<const int4*>(in + (row * W + iw) * C) + c16);
-        m[0] = __vmaxs4(m[0], (uint32_t)v.x);
-        m[1] = __vmaxs4(m[1], (uint32_t)v.y);
-        m[2] = __vmaxs4(m[2], (uint32_t)v.z);
-        m[3] = __vmaxs4(m[3], (uint32_t)v.w);
+        const uint32_t u[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cc <= 2) h[0][j] = __vmaxs4(h[0][j], u[j]);
+          if (cc >= 2) h[1][j] = __vmaxs4(h[1][j], u[j]);
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (rr <= 2) m[0][b][j] = __vmaxs4(m[0][b][j], h[b][j]);
+          if (rr >= 2) m[1][b][j] = __vmaxs4(m[1][b][j], h[b][j]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (oh0 + a >= OH) continue;
+      const size_t orow = static_cast<size_t>(PRo) + static_cast<size_t>(n) * (OH + PRo) + oh0 + a;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (ow0 + b >= OW) continue;
+        reinterpret_cast<int4*>(out + (orow * OW + ow0 + b) * C)[c16] =
+            make_int4((int)m[a][b][0], (int)m[a][b][1], (int)m[a][b][2], (int)m[a][b][3]);
       }
     }
-    const size_t orow = static_cast<size_t>(PRo) + static_cast<size_t>(n) * (OH + PRo) + oh;
-    reinterpret_cast<int4*>(out + (orow * OW + ow) * C)[c16] = make_int4((int)m[0], (int)m[1], (int)m[2], (int)m[3]);
   }
 }
 
@@ -326,32 +357,30 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
   }
   __syncthreads();
   if (!logits) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int o = warp; o < O; o += nwarps) {
+  // phase 2: FC.  fc_wT is the weight matrix pre-transposed on the host to [C/16][Opad][16 B] so that
+  // consecutive threads (= consecutive outputs) read consecutive 16-byte chunks; the pooled activations are
+  // broadcast from shared memory.  One thread = one output row for all images of the CTA, no shuffles.
+  const int Opad = (O + 63) & ~63;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) {
     int acc[kGapImgs];
 #pragma unroll
     for (int im = 0; im < kGapImgs; ++im) acc[im] = 0;
-    for (int k = lane * 16; k < C; k += 32 * 16) {
-      const int4 wv = __ldg(reinterpret_cast<const int4*>(fc_w + static_cast<size_t>(o) * C + k));
+#pragma unroll 4
+    for (int kc = 0; kc < C / 16; ++kc) {
+      const int4 wv = __ldg(reinterpret_cast<const int4*>(fc_w) + static_cast<size_t>(kc) * Opad + o);
 #pragma unroll
       for (int im = 0; im < kGapImgs; ++im) {
-        if (im < nimg) {
-          const int4 gv = *reinterpret_cast<const int4*>(sg + im * C + k);
-          acc[im] = __dp4a(wv.x, gv.x, acc[im]);
-          acc[im] = __dp4a(wv.y, gv.y, acc[im]);
-          acc[im] = __dp4a(wv.z, gv.z, acc[im]);
-          acc[im] = __dp4a(wv.w, gv.w, acc[im]);
-        }
+        const int4 gv = *reinterpret_cast<const int4*>(sg + im * C + kc * 16);
+        acc[im] = __dp4a(wv.x, gv.x, acc[im]);
+        acc[im] = __dp4a(wv.y, gv.y, acc[im]);
+        acc[im] = __dp4a(wv.z, gv.z, acc[im]);
+        acc[im] = __dp4a(wv.w, gv.w, acc[im]);
       }
     }
+    const float sc = __ldg(fc_scale + o), bi = __ldg(fc_bias + o);
 #pragma unroll
-    for (int im = 0; im < kGapImgs; ++im) {
-      int a = acc[im];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
-      if (lane == 0 && im < nimg)
-        logits[static_cast<size_t>(n0 + im) * O + o] = __fmaf_rn((float)a, __ldg(fc_scale + o), __ldg(fc_bias + o));
-    }
+    for (int im = 0; im < kGapImgs; ++im)
+      if (im < nimg) logits[static_cast<size_t>(n0 + im) * O + o] = __fmaf_rn((float)acc[im], sc, bi);
   }
 }
 
@@ -531,7 +560,7 @@ int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float 
 }
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
   DLQ_ARG(ctx, in.C % 16 == 0 && out.C == in.C && out.N == in.N, "maxpool geometry");
-  const size_t total = static_cast<size_t>(in.N) * out.H * out.W * (in.C / 16);
+  const size_t total = static_cast<size_t>(in.N) * ((out.H + 1) / 2) * ((out.W + 1) / 2) * (in.C / 16);
   maxpool_act_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR,
                                                                          out.H, out.W, out.PR);
   DLQ_CUDA(ctx, cudaGetLastError());
