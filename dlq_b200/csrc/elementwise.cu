@@ -589,8 +589,8 @@ extern "C" {
 
 int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int8_t* q) {
   if (!ctx) return DLQ_ERR_ARG;
+  if (n == 0) return DLQ_OK;   // empty input: nothing to do (pointers may be null)
   DLQ_ARG(ctx, x && q && scale > 0.f, "null pointer or non-positive scale");
-  if (n == 0) return DLQ_OK;
   DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
           "pointers must be 16-byte aligned");
   quantize_f32_i8_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(x, n, inv_scale(scale), q);
@@ -599,8 +599,8 @@ int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int
 }
 int dlq_dequantize_i8_f32(dlq_ctx* ctx, const int8_t* q, size_t n, float scale, float* x) {
   if (!ctx) return DLQ_ERR_ARG;
-  DLQ_ARG(ctx, x && q, "null pointer");
   if (n == 0) return DLQ_OK;
+  DLQ_ARG(ctx, x && q, "null pointer");
   DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
           "pointers must be 16-byte aligned");
   dequantize_i8_f32_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(q, n, scale, x);

@@ -371,6 +371,17 @@ void orc_conv2d_i8(const int8_t* x, int N, int C, int H, int W, const int8_t* w,
     }
 }
 
+/* QUANT_SPEC §4: standalone residual add of two int8 tensors with different scales */
+void orc_add_requant_i8(int8_t* y, float y_scale, const int8_t* x, float x_scale, size_t n, int relu, float out_scale) {
+  const float inv = orc_inv_scale(out_scale);
+  for (size_t i = 0; i < n; ++i) {
+    float t = (float)y[i] * y_scale;
+    t = fmaf((float)x[i], x_scale, t);
+    if (relu && t < 0.f) t = 0.f;
+    y[i] = quant1(t * inv, relu ? 0 : -128, 127);
+  }
+}
+
 /* max-pool on int8 (monotone => commutes with quantisation); geometry as K/maxpool2d.cu:14-40 */
 void orc_maxpool3x3s2p1_i8(const int8_t* x, int N, int C, int H, int W, int8_t* y) {
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;

@@ -111,6 +111,7 @@ typedef struct {
 /* int8 conv; acc_out (int32 NCHW, may be NULL) receives raw accumulators, y (int8 NCHW) the epilogue result */
 void orc_conv2d_i8(const int8_t* x, int N, int C, int H, int W, const int8_t* w, int OC, int kH, int kW, int sH,
                    int sW, int pH, int pW, const orc_epilogue* ep, int32_t* acc_out, int8_t* y);
+void orc_add_requant_i8(int8_t* y, float y_scale, const int8_t* x, float x_scale, size_t n, int relu, float out_scale);
 void orc_maxpool3x3s2p1_i8(const int8_t* x, int N, int C, int H, int W, int8_t* y);
 /* GAP: int32 sum -> (float)sum * scale_over_hw -> optional requant */
 void orc_gap_i8(const int8_t* x, int N, int C, int H, int W, float scale_over_hw, float inv_out_scale,

@@ -244,6 +244,14 @@ def conv2d_i8(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_mul=
     return acc, y
 
 
+def add_requant_i8(y, y_scale, x, x_scale, relu, out_scale):
+    y = np.ascontiguousarray(y, dtype=np.int8).copy()
+    x = np.ascontiguousarray(x, dtype=np.int8)
+    lib().orc_add_requant_i8(_p(y), C.c_float(y_scale), _p(x), C.c_float(x_scale), C.c_size_t(y.size), int(relu),
+                             C.c_float(out_scale))
+    return y
+
+
 def maxpool_i8(x):
     x = np.ascontiguousarray(x, dtype=np.int8)
     n, c, h, w = x.shape
