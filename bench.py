@@ -108,6 +108,7 @@ def cpu_oracle_rate(sample_images: int):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
     from dlq_b200 import synth
+    orc.lib().orc_set_num_threads(os.cpu_count() or 1)
     w = synth.make_weights(0, fill=orc.fill_f32)
     m = orc.I8Model(w, synth.load_act_scales(0))
     x = synth.make_input(0, sample_images, fill=orc.fill_f32)
@@ -125,6 +126,7 @@ def run_reference(args, rank: int, world: int):
     from dlq_b200 import synth
     w = synth.make_weights(0, fill=orc.fill_f32)
     m = orc.I8Model(w, synth.load_act_scales(0))
+    orc.lib().orc_set_num_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1
     threads = orc.lib().orc_num_threads()
     x1 = synth.make_input(0, threads, fill=orc.fill_f32)
     t0 = time.perf_counter()
@@ -141,7 +143,7 @@ def run_reference(args, rank: int, world: int):
     dt = time.perf_counter() - t0
     val = per_step * args.steps / dt
     sample = f"{per_step} of {args.batch} images per step (bounded CPU sample), CPU oracle port, OpenMP {threads} threads"
-    print(json.dumps({
+    print_json({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "s8", "data": "synthetic",
@@ -150,7 +152,7 @@ def run_reference(args, rank: int, world: int):
                            "this arm is the CPU oracle port"},
         "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 def run_ours(args, rank: int, local_rank: int, world: int):
@@ -270,12 +272,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                      "per_launch_ms": {n: round(float(v), 4) for n, v in zip(names, prof)}},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Route everything libraries print on fd 1 (e.g. the NCCL version banner) to stderr and return a writer
+    for the real stdout, so that stdout carries exactly one JSON line."""
+    real = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
+    global print_json
+
+    def print_json(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -152,6 +152,7 @@ void orc_mnist_mlp_forward(const float* x, const float* w1, const float* b1, con
                            int batch, int in_dim, int hid, int out_dim, float* hidden, float* out);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
