@@ -121,6 +121,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_epi_warps = (blockDim.x >> 5) - 4;
+  // Two MMA-issuing warps (1 and 3) split the M tiles of a super-tile: one issuer cannot keep the tensor pipe
+  // busy (loop / barrier overhead between tcgen05.mma is exposed), two interleaved issuers can.
+  const int n_issuers = p.MT >= 2 ? 2 : 1;
   const int n_blk = blockIdx.y;                 // output-channel tile
   const int n0 = n_blk * p.n_tile;
   const uint32_t acc_cols = static_cast<uint32_t>(p.MT) * p.n_tile;   // TMEM columns per accumulator stage
@@ -128,9 +131,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   while (tmem_cols < acc_cols * p.acc_stages) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.cluster); }
-    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], n_epi_warps); }
+    for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.cluster * n_issuers); }
+    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&acc_full[i], n_issuers); mbar_init(&acc_empty[i], n_epi_warps); }
     fence_mbar_init();
     tma_prefetch_desc(&tm0);
   }
@@ -201,20 +204,27 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+  } else if (warp == 1 || (warp == 3 && n_issuers == 2)) {
+    // ===================================================================== MMA issuers
     // The whole warp walks the loop (so the address arithmetic stays warp-uniform); one elected lane
     // issues.  Descriptors are advanced by adding to their low word (start address >> 4).
     const bool leader = elect_one();
+    const int issuer = (warp == 1) ? 0 : 1;
+    const int my_mt = p.MT / n_issuers;                 // tiles this issuer owns: [issuer*my_mt, +my_mt)
     const uint32_t idesc = umma_idesc_s8(kTileM, static_cast<uint32_t>(p.n_tile));
     const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT) >> 32);
     const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, B_SBO, LAYOUT) >> 32);
     const uint32_t a_lo_flags = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT));
     const uint32_t b_lo_flags =
         static_cast<uint32_t>(umma_smem_desc(0, ROWB == 16 ? static_cast<uint32_t>(p.n_tile) * 16u : 0u, B_SBO, LAYOUT));
+    // tcgen05.mma issue is the critical path of the whole kernel (probe/mma_rate.cu: the tensor pipe does not
+    // queue ahead, every cycle the issuing lane stalls is a cycle the pipe idles), so this loop is kept minimal:
+    // fully unrolled MMA groups per step, no per-step warp sync, weight-barrier waits only when weights stream.
     uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
     long long t_acc = 0, t_a = 0, t_b = 0;
     const long long t_begin = clock64();
+    bool first_pass = true;                          // resident weights: b_full is only waited for on the first pass
+    const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
     for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
       const int g0 = st * super_pos;
       const int v0 = g0 / p.Wp;
@@ -222,7 +232,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
       long long tw = clock64();
       mbar_wait(&acc_empty[cs], cph ^ 1u);
       t_acc += clock64() - tw;
-      const uint32_t d_base = tmem_base + cs * acc_cols;
+      const uint32_t d_base = tmem_base + cs * acc_cols + static_cast<uint32_t>(issuer * my_mt) * n_tile;
+      const uint32_t dacc[2] = {d_base, d_base + n_tile};
       for (int s = 0; s < p.n_sub; ++s) {
         tw = clock64();
         mbar_wait(&a_full[as], aph);
@@ -232,45 +243,51 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
             a_lo_flags + (smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) >> 4) + in_patch16;
         const int k_end = p.sub_step0[s + 1];
         for (int k = p.sub_step0[s]; k < k_end; ++k) {
-          tw = clock64();
-          mbar_wait(&b_full[bs], p.b_resident ? 0u : bph);
-          t_b += clock64() - tw;
-          tc_fence_after();
-          if (leader && !(p.dbg & 2)) {
+          if (!p.b_resident || first_pass) {
+            tw = clock64();
+            mbar_wait(&b_full[bs], p.b_resident ? 0u : bph);
+            t_b += clock64() - tw;
+            tc_fence_after();
+          }
+          if (leader) {
             const uint32_t b_lo = b_lo_flags + (smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes) >> 4);
-            uint32_t a_lo = a_lo_base + p.step_a16[k];
-            uint32_t d = d_base;
-            for (int mt = 0; mt < p.MT; ++mt) {
-#pragma unroll
-              for (int kk = 0; kk < K32; ++kk) {
-                const uint64_t ad = (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * kk);
-                const uint64_t bd = (static_cast<uint64_t>(b_hi) << 32) | (b_lo + (ROWB == 16 ? 0u : 2u * kk));
-                umma_i8(d, ad, bd, idesc, (k | kk) ? 1u : 0u);
+            const uint32_t a_lo = a_lo_base + p.step_a16[k] + static_cast<uint32_t>(issuer * my_mt) * TILE16;
+            if (!(p.dbg & 2)) {
+              // Fully unrolled, every operand a compile-time offset from (a_lo, b_lo, dacc[]) and the accumulate
+              // flag a compile-time constant: anything data-dependent between two tcgen05.mma (a predicate, a
+              // branch, an address multiply) costs ~25 cycles of tensor-pipe idle time (probe/mma_rate.cu "morph").
+              // kk outer / tile inner so consecutive MMAs hit different accumulators.
+#define DLQ_ISSUE_STEP(MTV, FIRSTV)                                                                              \
+  _Pragma("unroll") for (int kk = 0; kk < K32; ++kk) {                                                           \
+    _Pragma("unroll") for (int mt = 0; mt < (MTV); ++mt) {                                                       \
+      umma_i8(dacc[mt], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),                    \
+              (static_cast<uint64_t>(b_hi) << 32) | (b_lo + (ROWB == 16 ? 0u : 2u * kk)), idesc,                 \
+              ((FIRSTV) && kk == 0) ? 0u : 1u);                                                                  \
+    }                                                                                                            \
+  }
+              if (k == 0) {
+                if (my_mt == 2) { DLQ_ISSUE_STEP(2, true) } else { DLQ_ISSUE_STEP(1, true) }
+              } else {
+                if (my_mt == 2) { DLQ_ISSUE_STEP(2, false) } else { DLQ_ISSUE_STEP(1, false) }
               }
-              a_lo += TILE16;
-              d += static_cast<uint32_t>(p.n_tile);
+#undef DLQ_ISSUE_STEP
             }
             if (!p.b_resident) {   // weight stage free (in every CTA of the cluster) once these MMAs retire
               if (p.cluster > 1) umma_commit_multicast(&b_empty[bs], static_cast<uint16_t>((1u << p.cluster) - 1u));
               else umma_commit(&b_empty[bs]);
             }
           }
-          if (leader && (p.dbg & 2) && !p.b_resident) {
-            if (p.cluster > 1) umma_commit_multicast(&b_empty[bs], static_cast<uint16_t>((1u << p.cluster) - 1u));
-            else umma_commit(&b_empty[bs]);
-          }
-          __syncwarp();
           if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
         }
         if (leader) umma_commit(&a_empty[as]);     // sub-patch stage free
-        __syncwarp();
         if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
       }
       if (leader) umma_commit(&acc_full[cs]);      // accumulators ready for the epilogue
       __syncwarp();
+      first_pass = false;
       if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
-    if (p.dbg_times && leader) {
+    if (p.dbg_times && leader && issuer == 0) {
       long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
       d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_b;
     }

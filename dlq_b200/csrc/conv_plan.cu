@@ -252,7 +252,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 3072 /*alpha,beta,barriers*/ - 8 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
-  if (const char* e = getenv("DLQ_DBG_MT")) MT = std::max(1, atoi(e));
+  if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) MT = v; }
   int NR = 0;
   const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;
   for (;; MT >>= 1) {
