@@ -15,8 +15,8 @@
 //   through a UMMA descriptor whose start address is advanced by (a*Wp + b) pixel rows.  Every input
 //   byte crosses L2->SM once per super-tile instead of once per tap.
 //   Stride-2 convolutions use up to four parity planes, each loaded by TMA with elementStrides = 2.
-//   The 3-channel stem uses a 2x2 space-to-depth input (16 B per pixel, no swizzle) and pairs two
-//   horizontally adjacent pixels into one K=32 MMA through the descriptor's leading-byte-offset.
+//   The 3-channel stem uses a 2x2 space-to-depth input stored as 32-byte "pixel pairs" [p | p+1] (SW32 rows),
+//   so one K=32 MMA covers two horizontally adjacent taps.
 //   (All three addressing tricks are validated by probe/umma_probe.cu on a B200.)
 //
 // Warp roles (256 or 384 threads): warp 0 = activation-patch TMA producer, warp 1 = MMA issuer
@@ -85,18 +85,140 @@ __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
   return r;   // bytes (low->high): a, b, c, d
 }
 
+// ------------------------------------------------------------------------------------------------
+// MMA issuer (one elected lane of an issuing warp).  tcgen05.mma issue is the critical path of the whole
+// kernel: the tensor pipe does not queue ahead, so every cycle the issuing lane spends between two MMAs is
+// a cycle the pipe idles (probe/mma_rate.cu).  Hence: everything a compile-time offset from (a_lo, b_lo,
+// d0), constant accumulate flags (first step peeled), no data-dependent branch or multiply in the step
+// body, and separate instantiations for resident / streamed weights and 1 / 2 tiles per issuer.
+// ------------------------------------------------------------------------------------------------
+struct IssuerCtx {
+  uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *acc_empty;
+  const uint16_t* step_a16;     // shared-memory copy of the per-step A offsets
+  const int16_t* sub_step0;
+  uint32_t sA_u32, sB_u32, a_stage16, b_stage16;   // ring bases (shared window) and stage sizes in 16-byte units
+  uint32_t tmem_base, acc_cols, n_tile;
+  int n_sub, a_stages, b_stages, acc_stages, cluster, Wp, super_pos;
+  int st_begin, st_end, st_stride;
+  uint32_t tile_off16;          // this issuer's first tile, in 16-byte units down the patch
+  uint32_t d_off;               // this issuer's first accumulator column offset
+  bool leader;
+  int dbg;
+};
+
+template <int ROWB, int MYMT, bool FIRST>
+__device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_t a_lo, uint32_t b_lo, uint32_t d0,
+                                           uint32_t n_tile, uint32_t idesc) {
+  constexpr int K32 = ROWB / 32;
+  constexpr uint32_t TILE16 = kTileM * ROWB / 16;
+#pragma unroll
+  for (int kk = 0; kk < K32; ++kk) {
+#pragma unroll
+    for (int mt = 0; mt < MYMT; ++mt) {   // tile inner: consecutive MMAs hit different accumulators
+      umma_i8(d0 + (mt ? n_tile : 0u), (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),
+              (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc,
+              (FIRST && kk == 0) ? 0u : 1u);
+    }
+  }
+}
+
+template <int ROWB, int MYMT, bool RESIDENT>
+__device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out) {
+  constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
+  constexpr uint32_t A_SBO = 8u * ROWB;
+  constexpr uint32_t A_LBO = 0u;
+  constexpr uint32_t B_SBO = 8u * ROWB;
+  const uint32_t idesc = umma_idesc_s8(kTileM, c.n_tile);
+  const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT) >> 32);
+  const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, B_SBO, LAYOUT) >> 32);
+  const uint32_t a_flags = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT)) + (c.sA_u32 >> 4) + c.tile_off16;
+  const uint32_t b_flags =
+      static_cast<uint32_t>(umma_smem_desc(0, 0u, B_SBO, LAYOUT)) + (c.sB_u32 >> 4);
+  const uint16_t cta_mask = static_cast<uint16_t>((1u << c.cluster) - 1u);
+  uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+  long long t_acc = 0, t_a = 0, t_b = 0;
+  bool first_pass = true;
+  for (int st = c.st_begin; st < c.st_end; st += c.st_stride) {
+    const int g0 = st * c.super_pos;
+    const uint32_t in_patch16 = static_cast<uint32_t>(g0 - (g0 / c.Wp) * c.Wp) * (ROWB / 16);
+    long long tw = clock64();
+    mbar_wait(&c.acc_empty[cs], cph ^ 1u);
+    t_acc += clock64() - tw;
+    const uint32_t d0 = c.tmem_base + cs * c.acc_cols + c.d_off;
+    for (int s = 0; s < c.n_sub; ++s) {
+      tw = clock64();
+      mbar_wait(&c.a_full[as], aph);
+      t_a += clock64() - tw;
+      tc_fence_after();
+      const uint32_t a_base = a_flags + as * c.a_stage16 + in_patch16;
+      int k = c.sub_step0[s];
+      const int k_end = c.sub_step0[s + 1];
+      if (RESIDENT && first_pass) {               // weights arrive once; afterwards no weight barrier at all
+        for (int kw = k; kw < k_end; ++kw) {
+          tw = clock64();
+          mbar_wait(&c.b_full[kw], 0u);
+          t_b += clock64() - tw;
+        }
+        tc_fence_after();
+      }
+      if (s == 0) {                               // peeled first step of the super-tile: overwrites the accumulators
+        if (!RESIDENT) {
+          tw = clock64();
+          mbar_wait(&c.b_full[bs], bph);
+          t_b += clock64() - tw;
+          tc_fence_after();
+        }
+        if (c.leader) {
+          const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, true>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!RESIDENT) {
+            if (c.cluster > 1) umma_commit_multicast(&c.b_empty[bs], cta_mask);
+            else umma_commit(&c.b_empty[bs]);
+          }
+        }
+        if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
+        ++k;
+      }
+      for (; k < k_end; ++k) {
+        if (!RESIDENT) {
+          tw = clock64();
+          mbar_wait(&c.b_full[bs], bph);
+          t_b += clock64() - tw;
+          tc_fence_after();
+        }
+        if (c.leader) {
+          const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!RESIDENT) {
+            if (c.cluster > 1) umma_commit_multicast(&c.b_empty[bs], cta_mask);
+            else umma_commit(&c.b_empty[bs]);
+          }
+        }
+        if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
+      }
+      if (c.leader) umma_commit(&c.a_empty[as]);     // sub-patch stage free
+      if (++as == static_cast<uint32_t>(c.a_stages)) { as = 0; aph ^= 1u; }
+    }
+    if (c.leader) umma_commit(&c.acc_full[cs]);      // accumulators ready for the epilogue
+    __syncwarp();
+    first_pass = false;
+    if (++cs == static_cast<uint32_t>(c.acc_stages)) { cs = 0; cph ^= 1u; }
+  }
+  t_out[0] = t_acc; t_out[1] = t_a; t_out[2] = t_b;
+}
+
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha,beta: 2*n_tile f32]
 //   [epilogue staging: 8 * kEpiStageBytes][barriers][tmem slot]
 template <int ROWB>
 __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p) {
-  constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_NONE;
-  // descriptor strides: swizzled K-major: SBO = 8 rows; no-swizzle 16B pixels: SBO = 128 B, LBO = 16 B (next pixel)
-  constexpr uint32_t A_SBO = ROWB == 16 ? 128u : 8u * ROWB;
-  constexpr uint32_t A_LBO = ROWB == 16 ? 16u : 0u;
-  constexpr uint32_t B_SBO = ROWB == 16 ? 128u : 8u * ROWB;
-  constexpr int K32 = ROWB == 16 ? 1 : ROWB / 32;      // MMAs (K = 32) per step per tile
+  constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
+  // descriptor strides: swizzled K-major rows of ROWB bytes, SBO = 8 rows
+  constexpr uint32_t A_SBO = 8u * ROWB;
+  constexpr uint32_t A_LBO = 0u;
+  constexpr uint32_t B_SBO = 8u * ROWB;
+  constexpr int K32 = ROWB / 32;      // MMAs (K = 32) per step per tile
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   extern __shared__ uint8_t smem_raw[];
@@ -110,7 +232,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   float* s_alpha = reinterpret_cast<float*>(sB + static_cast<size_t>(p.b_stages) * b_stage_bytes);
   float* s_beta = s_alpha + p.n_tile;
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.n_tile);          // [epilogue warps][kEpiStageBytes]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 8 * kEpiStageBytes);
+  uint16_t* s_step_a16 = reinterpret_cast<uint16_t*>(s_stage + 8 * kEpiStageBytes);   // [kMaxSteps]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_step_a16 + kMaxSteps + 8);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_stages;
   uint64_t* b_full = a_empty + p.a_stages;
@@ -141,6 +264,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.n_steps; i += blockDim.x) s_step_a16[i] = p.step_a16[i];
   for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) {
     s_alpha[i] = p.alpha ? p.alpha[n0 + i] : 1.f;
     s_beta[i] = p.beta ? p.beta[n0 + i] : 0.f;
@@ -208,88 +332,30 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     // ===================================================================== MMA issuers
     // The whole warp walks the loop (so the address arithmetic stays warp-uniform); one elected lane
     // issues.  Descriptors are advanced by adding to their low word (start address >> 4).
-    const bool leader = elect_one();
+    IssuerCtx c;
+    c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.acc_full = acc_full; c.acc_empty = acc_empty;
+    c.step_a16 = s_step_a16; c.sub_step0 = p.sub_step0;
+    c.sA_u32 = smem_u32(sA); c.sB_u32 = smem_u32(sB); c.a_stage16 = a_stage_bytes >> 4; c.b_stage16 = b_stage_bytes >> 4;
+    c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.n_tile = static_cast<uint32_t>(p.n_tile);
+    c.n_sub = p.n_sub; c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.acc_stages = p.acc_stages; c.cluster = p.cluster;
+    c.Wp = p.Wp; c.super_pos = super_pos;
+    c.st_begin = static_cast<int>(blockIdx.x); c.st_end = st_end; c.st_stride = static_cast<int>(gridDim.x);
     const int issuer = (warp == 1) ? 0 : 1;
     const int my_mt = p.MT / n_issuers;                 // tiles this issuer owns: [issuer*my_mt, +my_mt)
-    const uint32_t idesc = umma_idesc_s8(kTileM, static_cast<uint32_t>(p.n_tile));
-    const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT) >> 32);
-    const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, B_SBO, LAYOUT) >> 32);
-    const uint32_t a_lo_flags = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT));
-    const uint32_t b_lo_flags =
-        static_cast<uint32_t>(umma_smem_desc(0, ROWB == 16 ? static_cast<uint32_t>(p.n_tile) * 16u : 0u, B_SBO, LAYOUT));
-    // tcgen05.mma issue is the critical path of the whole kernel (probe/mma_rate.cu: the tensor pipe does not
-    // queue ahead, every cycle the issuing lane stalls is a cycle the pipe idles), so this loop is kept minimal:
-    // fully unrolled MMA groups per step, no per-step warp sync, weight-barrier waits only when weights stream.
-    uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
-    long long t_acc = 0, t_a = 0, t_b = 0;
+    c.tile_off16 = static_cast<uint32_t>(issuer * my_mt) * TILE16;
+    c.d_off = static_cast<uint32_t>(issuer * my_mt) * static_cast<uint32_t>(p.n_tile);
+    c.leader = elect_one();
+    c.dbg = p.dbg;
+    long long tt[3] = {0, 0, 0};
     const long long t_begin = clock64();
-    bool first_pass = true;                          // resident weights: b_full is only waited for on the first pass
-    const uint32_t n_tile = static_cast<uint32_t>(p.n_tile);
-    for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
-      const int g0 = st * super_pos;
-      const int v0 = g0 / p.Wp;
-      const uint32_t in_patch16 = static_cast<uint32_t>(g0 - v0 * p.Wp) * (ROWB / 16);   // first position's offset
-      long long tw = clock64();
-      mbar_wait(&acc_empty[cs], cph ^ 1u);
-      t_acc += clock64() - tw;
-      const uint32_t d_base = tmem_base + cs * acc_cols + static_cast<uint32_t>(issuer * my_mt) * n_tile;
-      const uint32_t dacc[2] = {d_base, d_base + n_tile};
-      for (int s = 0; s < p.n_sub; ++s) {
-        tw = clock64();
-        mbar_wait(&a_full[as], aph);
-        t_a += clock64() - tw;
-        tc_fence_after();
-        const uint32_t a_lo_base =
-            a_lo_flags + (smem_u32(sA + static_cast<size_t>(as) * a_stage_bytes) >> 4) + in_patch16;
-        const int k_end = p.sub_step0[s + 1];
-        for (int k = p.sub_step0[s]; k < k_end; ++k) {
-          if (!p.b_resident || first_pass) {
-            tw = clock64();
-            mbar_wait(&b_full[bs], p.b_resident ? 0u : bph);
-            t_b += clock64() - tw;
-            tc_fence_after();
-          }
-          if (leader) {
-            const uint32_t b_lo = b_lo_flags + (smem_u32(sB + static_cast<size_t>(bs) * b_stage_bytes) >> 4);
-            const uint32_t a_lo = a_lo_base + p.step_a16[k] + static_cast<uint32_t>(issuer * my_mt) * TILE16;
-            if (!(p.dbg & 2)) {
-              // Fully unrolled, every operand a compile-time offset from (a_lo, b_lo, dacc[]) and the accumulate
-              // flag a compile-time constant: anything data-dependent between two tcgen05.mma (a predicate, a
-              // branch, an address multiply) costs ~25 cycles of tensor-pipe idle time (probe/mma_rate.cu "morph").
-              // kk outer / tile inner so consecutive MMAs hit different accumulators.
-#define DLQ_ISSUE_STEP(MTV, FIRSTV)                                                                              \
-  _Pragma("unroll") for (int kk = 0; kk < K32; ++kk) {                                                           \
-    _Pragma("unroll") for (int mt = 0; mt < (MTV); ++mt) {                                                       \
-      umma_i8(dacc[mt], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),                    \
-              (static_cast<uint64_t>(b_hi) << 32) | (b_lo + (ROWB == 16 ? 0u : 2u * kk)), idesc,                 \
-              ((FIRSTV) && kk == 0) ? 0u : 1u);                                                                  \
-    }                                                                                                            \
-  }
-              if (k == 0) {
-                if (my_mt == 2) { DLQ_ISSUE_STEP(2, true) } else { DLQ_ISSUE_STEP(1, true) }
-              } else {
-                if (my_mt == 2) { DLQ_ISSUE_STEP(2, false) } else { DLQ_ISSUE_STEP(1, false) }
-              }
-#undef DLQ_ISSUE_STEP
-            }
-            if (!p.b_resident) {   // weight stage free (in every CTA of the cluster) once these MMAs retire
-              if (p.cluster > 1) umma_commit_multicast(&b_empty[bs], static_cast<uint16_t>((1u << p.cluster) - 1u));
-              else umma_commit(&b_empty[bs]);
-            }
-          }
-          if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
-        }
-        if (leader) umma_commit(&a_empty[as]);     // sub-patch stage free
-        if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
-      }
-      if (leader) umma_commit(&acc_full[cs]);      // accumulators ready for the epilogue
-      __syncwarp();
-      first_pass = false;
-      if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
+    if (p.b_resident) {
+      if (my_mt == 2) run_issuer<ROWB, 2, true>(c, tt); else run_issuer<ROWB, 1, true>(c, tt);
+    } else {
+      if (my_mt == 2) run_issuer<ROWB, 2, false>(c, tt); else run_issuer<ROWB, 1, false>(c, tt);
     }
-    if (p.dbg_times && leader && issuer == 0) {
+    if (p.dbg_times && c.leader && issuer == 0) {
       long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
-      d[0] = clock64() - t_begin; d[1] = t_acc; d[2] = t_a; d[3] = t_b;
+      d[0] = clock64() - t_begin; d[1] = tt[0]; d[2] = tt[1]; d[3] = tt[2];
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps

@@ -79,7 +79,8 @@ void make_schedule(const dlq_conv_weights* w, std::vector<SubDesc>& subs, std::v
     case CONV_STEM:
       // 7x7/s2/p3 over 3 channels == 4x4/s1 over the 2x2 space-to-depth image (16 B per pixel):
       // input row 2*oh - 3 + kh = 2*(oh - 2) + (kh + 1)  ->  s2d row oh - 2 + a, a = (kh+1)/2, dy = (kh+1)%2.
-      subs.push_back({0, -2, -2});
+      // the input tensor carries its horizontal padding physically (2 left, 1 right), so the column origin is 0
+      subs.push_back({0, 0, -2});
       for (int a = 0; a < 4; ++a)
         for (int bp = 0; bp < 2; ++bp) steps.push_back({0, a, bp, 0, a, 2 * bp});
       break;
@@ -90,6 +91,7 @@ inline uint32_t swz_off(uint32_t row, uint32_t kbyte, uint32_t row_bytes) {
   const uint32_t lin = row * row_bytes + kbyte;
   if (row_bytes == 128) return lin ^ (((lin >> 7) & 7u) << 4);
   if (row_bytes == 64) return lin ^ (((lin >> 7) & 3u) << 4);
+  if (row_bytes == 32) return lin ^ (((lin >> 7) & 1u) << 4);
   return lin;
 }
 
@@ -117,7 +119,7 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
   out->OC = OC; out->IC = IC; out->kH = kH; out->kW = kW; out->sH = sH; out->sW = sW; out->pH = pH; out->pW = pW;
   out->device = ctx->device;
   if (IC == 3 && kH == 7 && sH == 2 && pH == 3) {
-    out->kind = CONV_STEM; out->rowb = 16; out->kb = 1;
+    out->kind = CONV_STEM; out->rowb = 32; out->kb = 1;
   } else {
     DLQ_ARG(ctx, IC == 64 || (IC > 0 && IC % 128 == 0), "IC must be 64 or a multiple of 128 (or the 3-channel 7x7/s2/p3 stem)");
     out->rowb = IC == 64 ? 64 : 128;
@@ -141,7 +143,7 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
   make_schedule(out, subs, steps);
   DLQ_ARG(ctx, static_cast<int>(steps.size()) <= kMaxSteps && subs.size() <= 16, "too many K steps for one conv");
   out->n_steps = static_cast<int>(steps.size());
-  out->step_bytes = out->kind == CONV_STEM ? out->n_tile * 32u : static_cast<uint32_t>(out->n_tile) * out->rowb;
+  out->step_bytes = static_cast<uint32_t>(out->n_tile) * out->rowb;
   out->q_oihw.assign(wq, wq + static_cast<size_t>(OC) * IC * kH * kW);
 
   const int n_tiles = OC / out->n_tile;
@@ -156,14 +158,14 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
       for (int n = 0; n < out->n_tile; ++n) {
         const int o = nt * out->n_tile + n;
         if (out->kind == CONV_STEM) {
-          // image [kchunk j (2)][n][16 B]; 16 B = [dy][dx][c4]; pixel column block b = 2*bp + j
+          // 32-byte row = pixel pair (b = 2*bp + j, j = 0,1); 16 B per pixel = [dy][dx][c4]
           for (int j = 0; j < 2; ++j)
             for (int t = 0; t < 16; ++t) {
               const int dy = t >> 3, dx = (t >> 2) & 1, c = t & 3;
               const int kh = 2 * sd.kh + dy - 1, kw = 2 * (2 * sd.kw + j) + dx - 1;
               int8_t v = 0;
               if (c < 3 && kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = W(o, c, kh, kw);
-              dst[static_cast<size_t>(j) * out->n_tile * 16 + n * 16 + t] = static_cast<uint8_t>(v);
+              dst[swz_off(n, j * 16 + t, 32)] = static_cast<uint8_t>(v);
             }
         } else {
           for (int k = 0; k < out->rowb; ++k)
@@ -205,10 +207,11 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       p.Pv = (in.H + in.PR) / 2;
       break;
     case CONV_STEM:
-      DLQ_ARG(ctx, in.C == 16 && in.PR >= 2, "stem expects the 2x2 space-to-depth input (16 B/pixel, PR >= 2)");
+      DLQ_ARG(ctx, in.C == 32 && in.PR >= 2 && in.W > 3,
+              "stem expects the paired 2x2 space-to-depth input (32 B/pixel, W/2+3 columns, PR >= 2)");
       p.Ho = in.H + 3 - 4 + 1;
-      p.Wo = in.W + 3 - 4 + 1;
-      p.Wp = in.W + 3;
+      p.Wo = in.W - 3;
+      p.Wp = in.W;
       p.Pv = in.H + in.PR;
       break;
   }
@@ -232,7 +235,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   for (int k = 0; k < p.n_steps; ++k) {
     const int sh = steps[k].da * p.Wp + steps[k].db;
     p.step_a16[k] = static_cast<uint16_t>(sh * rowb / 16);
-    maxshift = std::max(maxshift, sh + (w->kind == CONV_STEM ? 1 : 0));
+    maxshift = std::max(maxshift, sh);
   }
   for (int s = 0; s < p.n_sub; ++s) {
     p.sub_c0[s] = static_cast<int16_t>(subs[s].c0);
@@ -319,7 +322,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   cuuint32_t estr[3] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es)};
   const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+                                              : CU_TENSOR_MAP_SWIZZLE_32B;
   const CUresult r = enc(&L->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, in.ptr, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -345,7 +348,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   L->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_tiles), 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
-            2 * sizeof(float) * p.n_tile + 8 * kEpiStageBytes + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
+            2 * sizeof(float) * p.n_tile + 8 * kEpiStageBytes + 2 * (kMaxSteps + 8) + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
   return DLQ_OK;
 }
 
@@ -387,7 +390,7 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {
   switch (L.rowb) {
-    case 16: return launch_t<16>(ctx, L);
+    case 32: return launch_t<32>(ctx, L);
     case 64: return launch_t<64>(ctx, L);
     case 128: return launch_t<128>(ctx, L);
   }

@@ -198,7 +198,7 @@ int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, con
   in.N = N; in.PR = conv_required_in_pr(w);
   if (w->kind == CONV_STEM) {
     DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
-    in.H = H / 2; in.W = W / 2; in.C = 16;
+    in.H = H / 2; in.W = W / 2 + 3; in.C = 32;
   } else {
     in.H = H; in.W = W; in.C = C;
   }
@@ -271,7 +271,7 @@ static int plan_act(dlq_ctx* ctx, const dlq_act* x, const dlq_conv_weights* w, c
     out = to_act(y);
   } else {
     out.N = in.N; out.C = w->OC; out.PR = 0;
-    if (w->kind == CONV_STEM) { out.H = in.H; out.W = in.W; }
+    if (w->kind == CONV_STEM) { out.H = in.H; out.W = in.W - 3; }
     else conv_out_dims(w, in.H, in.W, &out.H, &out.W);
   }
   if (residual) res = to_act(residual);
@@ -511,7 +511,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   }
   // ---- activation buffers
   const int N = max_batch;
-  int rc = alloc_act(m.get(), m->a_in, N, 112, 112, 16, 2);
+  int rc = alloc_act(m.get(), m->a_in, N, 112, 115, 32, 2);
   if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_stem, N, 112, 112, 64, 0);
   if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_pool, N, 56, 56, 64, 1);
   int hw = 56;

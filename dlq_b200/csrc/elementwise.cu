@@ -174,13 +174,16 @@ __global__ void nhwc_to_nchw_i32_kernel(const int32_t* __restrict__ x, int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// stem input: [N,3,H,W] -> 2x2 space-to-depth, 16 B per s2d pixel = [dy][dx][c0,c1,c2,0], PR zero rows
-// One thread per s2d pixel: 6 float2 (or 6 char2) loads, one 16-byte store.
+// stem input: [N,3,H,W] -> 2x2 space-to-depth, 16 B per s2d pixel = [dy][dx][c0,c1,c2,0], stored as 32-byte
+// PAIRS [pixel p | pixel p+1] with the horizontal conv padding physically present: a row holds W/2+3 pairs for
+// p = -2 .. W/2 (out-of-range pixels are zero; those halves are never written and keep the memset zero).
+// One K=32 MMA then covers two horizontally adjacent taps from a normal SWIZZLE_32B K-major row.
+// One thread per s2d pixel: 6 float2 (or 6 char2) loads, two 16-byte stores (first half of pair p+2... see below).
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool QUANT>
 __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
                                 float inv_s) {
-  const int H2 = H / 2, W2 = W / 2;
+  const int H2 = H / 2, W2 = W / 2, WP = W2 + 3;
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -208,7 +211,10 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
     o.y = (int)pack4(q[0][1][0], q[0][1][1], q[0][1][2], 0);
     o.z = (int)pack4(q[1][0][0], q[1][0][1], q[1][0][2], 0);
     o.w = (int)pack4(q[1][1][0], q[1][1][1], q[1][1][2], 0);
-    reinterpret_cast<int4*>(a)[row * W2 + w2] = o;
+    // pair index j holds pixels (j-2, j-1): pixel w2 is the first half of pair w2+2 and the second half of pair w2+1
+    int4* prow = reinterpret_cast<int4*>(a) + (row * WP) * 2;
+    prow[(w2 + 2) * 2 + 0] = o;
+    prow[(w2 + 1) * 2 + 1] = o;
   }
 }
 
@@ -545,15 +551,15 @@ int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32
   return DLQ_OK;
 }
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a) {
-  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 && a.C == 16, "stem s2d geometry");
-  const size_t total = static_cast<size_t>(N) * a.H * a.W;
+  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
+  const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
   stem_s2d_kernel<int8_t, false><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
 int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a) {
-  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 && a.C == 16, "stem s2d geometry");
-  const size_t total = static_cast<size_t>(N) * a.H * a.W;
+  DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
+  const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
   stem_s2d_kernel<float, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;

@@ -98,7 +98,8 @@ int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, con
  * row-padded NHWC int8:  [PR zero rows][image 0: H rows of W*C bytes][PR zero rows][image 1] ...
  * The zero rows are the vertical padding; the caller zero-fills the buffer once (dlq_act_bytes) and the
  * kernels never write them.  x->PR must be >= dlq_conv_required_pad_rows(w); for stride-2 convs H+PR must be
- * even; the 3-channel stem takes the 2x2 space-to-depth image (H/2 x W/2 x 16 B, see dlq_stem_pack_input_i8). */
+ * even; the 3-channel stem takes the paired 2x2 space-to-depth image (H/2 rows x (W/2+3) pixel pairs x 32 B,
+ * produced by dlq_stem_pack_input_i8). */
 typedef struct {
   int8_t* ptr; /* device */
   int N, H, W, C, PR;

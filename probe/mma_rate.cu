@@ -148,11 +148,72 @@ __global__ void __launch_bounds__(128, 1) mma_multi(int n, int iters, int W, lon
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// TMEM read-out test: 4 warps (one per lane quarter) each issue `iters` tcgen05.ld.32x32b.x32 (4 KB per warp
+// instruction); optionally one more warp issues MMAs (N=64) at the same time into other TMEM columns.
+__global__ void __launch_bounds__(160, 1) tmem_ld_rate(int iters, int with_mma, int mma_iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc(&slot, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const int warp = threadIdx.x >> 5;
+  long long t0 = clock64();
+  uint32_t sink = 0;
+  if (warp < 4) {
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int i = 0; i < iters; ++i) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(taddr + ((i & 3) * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) sink ^= v[j];
+    }
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+  } else if (with_mma) {
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_s8(128, 64);
+    const uint64_t ad0 = umma_smem_desc(smem_u32(smem), 0, 1024, UMMA_SWZ_128B);
+    const uint64_t bd0 = umma_smem_desc(smem_u32(smem + 64 * 1024), 0, 1024, UMMA_SWZ_128B);
+    for (int i = 0; i < mma_iters; i += 4) {
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_i8(tmem + 256, ad0 + 2u * j, bd0 + 2u * j, idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    if (blockIdx.x == 0 && leader) out[1] = t1 - t0;
+  }
+  if (sink == 0x12345678u) out[2] = sink;
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
+}
+
 int main() {
   long long* d;
-  cudaMalloc(&d, 16);
+  cudaMalloc(&d, 64);
   cudaFuncSetAttribute(mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 8192;
+  cudaFuncSetAttribute(tmem_ld_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int with_mma : {0, 1}) {
+    cudaMemset(d, 0, 32);
+    tmem_ld_rate<<<148, 160, 200 * 1024>>>(2048, with_mma, 4096, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
+    long long h[2];
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("tmem_ld 32x32b.x32 x 4 warps: %.1f cyc per 16 KB (all 4 warps) -> %.1f B/cyc/SM; concurrent MMA(N=64): %s %.1f cyc/MMA\n", (double)h[0] / 2048, 16384.0 * 2048 / h[0], with_mma ? "yes" : "no", with_mma ? (double)h[1] / 4096 : 0.0);
+  }
   cudaFuncSetAttribute(mma_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int n : {64, 128})
     for (int W : {1, 2, 4}) {

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--exact", action="store_true")
     args = ap.parse_args()
     import torch
     import dlq_b200
@@ -53,14 +54,14 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.int8, device="cuda")
     rows = []
     for name, IC, H, OC, k, s, p, has_res in SHAPES:
-        if args.only and args.only not in name:
+        if args.only and (args.only != name if args.exact else args.only not in name):
             continue
         OH = (H + 2 * p - k) // s + 1
         wq = rng.integers(-127, 128, (OC, IC, k, k), dtype=np.int8)
         w = ctx.pack_conv_weights_i8(wq, s, p)
         pr = ctx.required_pad_rows(w)
         if IC == 3:
-            xbuf, xa = ctx.new_act(B, H // 2, H // 2, 16, pr)
+            xbuf, xa = ctx.new_act(B, H // 2, H // 2 + 3, 32, pr)
         else:
             xbuf, xa = ctx.new_act(B, H, H, IC, pr)
         xbuf.random_(-128, 127)     # pad rows too: irrelevant for timing
