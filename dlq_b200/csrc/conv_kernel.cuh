@@ -33,8 +33,12 @@ namespace dlq {
 constexpr int kMaxSteps = 40;    // K steps (tap x channel-block) per conv
 constexpr int kMaxPlanes = 4;
 constexpr int kTileM = 128;
-constexpr int kEpiStageRow = 80;                       // bytes per staged row (64 B payload + pad: conflict-free STS.128)
-constexpr int kEpiStageBytes = 32 * kEpiStageRow;      // per epilogue warp
+constexpr int kEpiStageRow = 64;                       // bytes per staged row; 16-byte chunk q of row r lives at chunk
+                                                       // q ^ ((r >> 1) & 3): conflict-free both row-per-lane and coalesced
+constexpr int kEpiStageBytes = 32 * kEpiStageRow;      // per staging slot (one unit: 32 rows x 64 channels)
+__device__ __forceinline__ int epi_stage_off(int row, int chunk) {
+  return row * kEpiStageRow + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
 
 struct ConvKernelParams {
   // virtual output space
@@ -73,6 +77,7 @@ struct ConvKernelParams {
   int8_t* out;            // row-padded NHWC int8
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
+  uint32_t wp_magic, pv_magic;   // floor(2^32/d)+1 for d = Wp, Pv (exact for positions < 2^24); 0 = use hardware division
   int dbg;                // tuning experiments only: 1 = skip TMEM loads, 2 = skip MMA issue, 4 = skip A loads
   long long* dbg_times;   // optional [gridDim.x*gridDim.y][8] cycle counters (tuning): see conv_plan.cu
 };
@@ -207,9 +212,185 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
   t_out[0] = t_acc; t_out[1] = t_a; t_out[2] = t_b;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue (8 warps).  A "unit" is (M tile, 64-channel block): per unit a warp turns its 32 accumulator rows x 64
+// int32 into 32 x 64 int8.  Units are processed in PAIRS so that two tcgen05.ld are in flight and - when the two
+// units are the same channel block of two tiles - every alpha/beta shared-memory read serves both.
+// Global traffic goes through per-warp staging slots (one per unit of the pair) so that every LDG/STG covers whole
+// 64-byte pixel rows: the residual rows of the NEXT pair are prefetched into the slots with cp.async (no registers
+// in flight, latency hidden behind the accumulator wait), read back row-per-lane, and the results are staged
+// row-per-lane in the same slot, read back coalesced and stored.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kInvalidPix = 0xFFFFFFFFu;
+
+struct EpiCtx {
+  const float* s_alpha;
+  const float* s_beta;
+  uint8_t* slots;          // this warp's staging: [2][32 rows][kEpiStageRow]
+  int lane, crow, cq;      // coalesced phase: row within a group of 8, 16-byte quarter
+  int out_pitch, res_pitch, n0;
+  uint32_t relu_mask;      // 0xFFFFFFFF: ReLU (negative bytes -> 0), 0: none
+  float res_mul;
+};
+
+__device__ __forceinline__ bool decode_pos(const ConvKernelParams& p, int g, int& n, int& r, int& x) {
+  int vrow;
+  if (p.wp_magic) {
+    vrow = static_cast<int>(__umulhi(static_cast<uint32_t>(g), p.wp_magic));
+    n = static_cast<int>(__umulhi(static_cast<uint32_t>(vrow), p.pv_magic));
+  } else {
+    vrow = g / p.Wp;
+    n = vrow / p.Pv;
+  }
+  x = g - vrow * p.Wp;
+  r = vrow - n * p.Pv;
+  return (x < p.Wo) && (r < p.Ho) && (n < p.N);
+}
+
+// cp.async the 32 residual rows (64 B each) of one unit into a staging slot; rows outside the tensor are zero-filled
+__device__ __forceinline__ void epi_prefetch_res(const ConvKernelParams& p, const EpiCtx& e, int slot, int g_own, int c0) {
+  int n, r, x;
+  const bool valid = decode_pos(p, g_own, n, r, x);
+  const uint32_t rpix = valid ? static_cast<uint32_t>((p.res_PR + n * e.res_pitch + r) * p.Wo + x) : kInvalidPix;
+  uint8_t* base = e.slots + slot * kEpiStageBytes;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int srow = 8 * j + e.crow;
+    const uint32_t rp = __shfl_sync(0xffffffffu, rpix, srow);
+    const bool ok = rp != kInvalidPix;
+    const int8_t* src = p.residual + (ok ? static_cast<size_t>(rp) * p.OC + e.n0 + c0 + e.cq * 16 : 0);
+    cp_async16_zfill(smem_u32(base + epi_stage_off(srow, e.cq)), src, ok ? 16u : 0u);
+  }
+}
+
+// two independent round-to-nearest fp32 FMAs in one instruction (sm_100 FFMA2); bit-identical to two fmaf
+__device__ __forceinline__ void fma2_rn(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
+template <bool HAS_RES, int NU, bool SAME_CB, bool ACC_OUT = false>
+__device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCtx& e, const uint32_t (&taddr)[2],
+                                          const int (&c0)[2], const int (&g_own)[2], bool release_acc,
+                                          uint64_t* acc_empty_bar) {
+  uint32_t opix[NU];
+  size_t dpix[NU];
+  bool valid[NU];
+#pragma unroll
+  for (int u = 0; u < NU; ++u) {
+    int n, r, x;
+    valid[u] = decode_pos(p, g_own[u], n, r, x);
+    opix[u] = valid[u] ? static_cast<uint32_t>((p.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
+    dpix[u] = ACC_OUT ? (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x : 0;
+  }
+  uint8_t* my_row[NU];    // own staged row (row = lane); chunk q sits at my_row + ((q ^ my_swz) << 4)
+  const int my_swz = (e.lane >> 1) & 3;
+#pragma unroll
+  for (int u = 0; u < NU; ++u) my_row[u] = e.slots + u * kEpiStageBytes + e.lane * kEpiStageRow;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint32_t v[NU][32];
+#pragma unroll
+    for (int u = 0; u < NU; ++u) tmem_ld_32x32b_x32(taddr[u] + h * 32, v[u]);
+    int4 rv[NU][2];
+    if (HAS_RES) {
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        rv[u][0] = *reinterpret_cast<const int4*>(my_row[u] + (((2 * h) ^ my_swz) << 4));
+        rv[u][1] = *reinterpret_cast<const int4*>(my_row[u] + (((2 * h + 1) ^ my_swz) << 4));
+      }
+    }
+    tmem_ld_wait();
+    if (release_acc && h == 1) {      // accumulators are in registers: hand the TMEM stage back to the MMA warps
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) mbar_arrive(acc_empty_bar);
+    }
+    if (ACC_OUT) {                    // raw accumulators (parity / debug entry points only)
+#pragma unroll
+      for (int u = 0; u < NU; ++u)
+        if (valid[u]) {
+          int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix[u] * p.OC + e.n0 + c0[u] + h * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_int4((int)v[u][4 * j], (int)v[u][4 * j + 1], (int)v[u][4 * j + 2], (int)v[u][4 * j + 3]);
+        }
+    }
+    uint32_t packed[NU][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 al[NU], be[NU];
+      al[0] = reinterpret_cast<const float4*>(e.s_alpha + c0[0] + h * 32)[j];
+      be[0] = reinterpret_cast<const float4*>(e.s_beta + c0[0] + h * 32)[j];
+      if (NU == 2) {
+        if (SAME_CB) { al[NU - 1] = al[0]; be[NU - 1] = be[0]; }
+        else {
+          al[NU - 1] = reinterpret_cast<const float4*>(e.s_alpha + c0[NU - 1] + h * 32)[j];
+          be[NU - 1] = reinterpret_cast<const float4*>(e.s_beta + c0[NU - 1] + h * 32)[j];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NU; ++u) {
+        float t0, t1, t2, t3;
+        fma2_rn(t0, t1, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 0])),
+                static_cast<float>(static_cast<int32_t>(v[u][4 * j + 1])), al[u].x, al[u].y, be[u].x, be[u].y);
+        fma2_rn(t2, t3, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 2])),
+                static_cast<float>(static_cast<int32_t>(v[u][4 * j + 3])), al[u].z, al[u].w, be[u].z, be[u].w);
+        if (HAS_RES) {
+          const uint32_t w = reinterpret_cast<const uint32_t*>(rv[u])[j];
+          fma2_rn(t0, t1, static_cast<float>(static_cast<int8_t>(w)), static_cast<float>(static_cast<int8_t>(w >> 8)),
+                  e.res_mul, e.res_mul, t0, t1);
+          fma2_rn(t2, t3, static_cast<float>(static_cast<int8_t>(w >> 16)), static_cast<float>(static_cast<int8_t>(w >> 24)),
+                  e.res_mul, e.res_mul, t2, t3);
+        }
+        const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2), __float2int_rn(t3));
+        // ReLU on the packed bytes: replicate each byte's sign (PRMT mode 8+i) and clear the negative ones
+        uint32_t sgn;
+        asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(sgn) : "r"(q));
+        asm("lop3.b32 %0, %1, %2, %3, 0x70;" : "=r"(packed[u][j]) : "r"(q), "r"(sgn), "r"(e.relu_mask));   // q & ~(sgn & mask)
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < NU; ++u) {
+      *reinterpret_cast<int4*>(my_row[u] + (((2 * h) ^ my_swz) << 4)) =
+          make_int4((int)packed[u][0], (int)packed[u][1], (int)packed[u][2], (int)packed[u][3]);
+      *reinterpret_cast<int4*>(my_row[u] + (((2 * h + 1) ^ my_swz) << 4)) =
+          make_int4((int)packed[u][4], (int)packed[u][5], (int)packed[u][6], (int)packed[u][7]);
+    }
+  }
+  __syncwarp();
+  if (p.out) {
+    // all shuffles, then all (unconditional) staged reads, then the predicated stores: no serialised
+    // shuffle -> load -> store chains
+    uint32_t op[NU][4];
+    int4 val[NU][4];
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[u][j] = __shfl_sync(0xffffffffu, opix[u], 8 * j + e.crow);
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        val[u][j] = *reinterpret_cast<const int4*>(e.slots + u * kEpiStageBytes + epi_stage_off(8 * j + e.crow, e.cq));
+#pragma unroll
+    for (int u = 0; u < NU; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (op[u][j] != kInvalidPix)
+          *(reinterpret_cast<int4*>(p.out + static_cast<size_t>(op[u][j]) * p.OC + e.n0 + c0[u]) + e.cq) = val[u][j];
+  }
+  __syncwarp();
+}
+
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha,beta: 2*n_tile f32]
-//   [epilogue staging: 8 * kEpiStageBytes][barriers][tmem slot]
+//   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
 template <int ROWB>
 __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p) {
@@ -232,7 +413,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   float* s_alpha = reinterpret_cast<float*>(sB + static_cast<size_t>(p.b_stages) * b_stage_bytes);
   float* s_beta = s_alpha + p.n_tile;
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.n_tile);          // [epilogue warps][kEpiStageBytes]
-  uint16_t* s_step_a16 = reinterpret_cast<uint16_t*>(s_stage + 8 * kEpiStageBytes);   // [kMaxSteps]
+  uint16_t* s_step_a16 = reinterpret_cast<uint16_t*>(s_stage + 16 * kEpiStageBytes);   // [kMaxSteps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_step_a16 + kMaxSteps + 8);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_stages;
@@ -359,119 +540,90 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
-    // Work unit: (M tile, 64-column block); the two warp groups take alternate units, the four warps of a
-    // group own the four TMEM lane quarters.  Per unit a warp turns 32 rows x 64 int32 accumulators into
-    // 32 x 64 int8.  Global traffic goes through a per-warp smem staging tile so that every LDG/STG
-    // instruction covers whole 64-byte pixel rows (8 rows x 64 B per instruction) instead of 32 scattered
-    // 16-byte pieces: residual rows are loaded coalesced -> staged -> read back row-per-lane; results are
-    // staged row-per-lane -> read back coalesced -> stored.
+    // The two warp groups take alternate units; the four warps of a group own the four TMEM lane quarters.
     const int ew = warp - 4;
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
     const int n_groups = n_epi_warps >> 2;
     const int grp = ew >> 2;
     const int row = quarter * 32 + lane;                // accumulator row within the tile
     const bool has_res = p.residual != nullptr;
-    const int out_pitch = p.Ho + p.out_PR, res_pitch = p.Ho + p.res_PR;
-    const uint32_t relu_floor = p.relu ? 0u : 0x80808080u;   // per-byte signed max with 0 (ReLU) or -128 (no-op)
-    const float res_mul = p.res_mul;
     const int cblocks = p.n_tile >> 6;
     const int n_units = p.MT * cblocks;
-    uint8_t* stage = s_stage + ew * kEpiStageBytes;     // [32 rows][kEpiStageRow bytes]
-    uint8_t* my_row = stage + lane * kEpiStageRow;
-    const int crow = lane >> 2, cq = lane & 3;          // coalesced phase: row within a group of 8, 16-byte quarter
-    constexpr uint32_t kInvalid = 0xFFFFFFFFu;
+    const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per super-tile: grp, grp + n_groups, ...
+    const int upp = p.acc_out ? 1 : 2;                  // units per pass (raw-accumulator output: one at a time)
+    const int n_pairs = (upw + upp - 1) / upp;
+    EpiCtx e;
+    e.s_alpha = s_alpha; e.s_beta = s_beta;
+    e.slots = s_stage + ew * 2 * kEpiStageBytes;
+    e.lane = lane; e.crow = lane >> 2; e.cq = lane & 3;
+    e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = n0;
+    e.relu_mask = p.relu ? 0xFFFFFFFFu : 0u;
+    e.res_mul = p.res_mul;
+    auto prefetch_pair = [&](int st, int pi) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = upp * pi + u;
+        if (u < upp && k < upw) {
+          const int unit = grp + k * n_groups;
+          const int mt = unit / cblocks, cb = unit - mt * cblocks;
+          epi_prefetch_res(p, e, u, st * super_pos + mt * kTileM + row, cb << 6);
+        }
+      }
+      cp_async_commit();
+    };
     uint32_t cs = 0, cph = 0;
     long long t_wait = 0;
     const long long t_begin = clock64();
+    if (has_res && static_cast<int>(blockIdx.x) < st_end && n_pairs > 0) prefetch_pair(blockIdx.x, 0);
     for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
       const long long tw = clock64();
       mbar_wait(&acc_full[cs], cph);
       t_wait += clock64() - tw;
       tc_fence_after();
-      for (int unit = (p.dbg & 1) ? n_units : grp; unit < n_units; unit += n_groups) {
-        const int mt = unit / cblocks, c0 = (unit - mt * cblocks) << 6;
-        const int g = st * super_pos + mt * kTileM + row;
-        const int vrow = g / p.Wp, x = g - vrow * p.Wp;
-        const int n = vrow / p.Pv, r = vrow - n * p.Pv;
-        const bool valid = (x < p.Wo) && (r < p.Ho) && (n < p.N);
-        const uint32_t opix = valid ? static_cast<uint32_t>((p.out_PR + n * out_pitch + r) * p.Wo + x) : kInvalid;
-        const uint32_t rpix = valid ? static_cast<uint32_t>((p.res_PR + n * res_pitch + r) * p.Wo + x) : kInvalid;
-        const uint32_t taddr = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile + c0 +
-                               (static_cast<uint32_t>(quarter * 32) << 16);
-        if (has_res) {
+      const int np = (p.dbg & 1) ? 0 : n_pairs;
+      for (int pi = 0; pi < np; ++pi) {
+        uint32_t taddr[2];
+        int c0[2], g_own[2];
+        const int nu = (2 * pi + 1 < upw && !p.acc_out) ? 2 : 1;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int srow = 8 * j + crow;
-            const uint32_t rp = __shfl_sync(0xffffffffu, rpix, srow);
-            int4 v = make_int4(0, 0, 0, 0);
-            if (rp != kInvalid)
-              v = __ldg(reinterpret_cast<const int4*>(p.residual + static_cast<size_t>(rp) * p.OC + n0 + c0) + cq);
-            *reinterpret_cast<int4*>(stage + srow * kEpiStageRow + cq * 16) = v;
-          }
+        for (int u = 0; u < 2; ++u) {
+          const int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
+          const int mt = unit / cblocks, cb = unit - mt * cblocks;
+          c0[u] = cb << 6;
+          g_own[u] = st * super_pos + mt * kTileM + row;
+          taddr[u] = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile + c0[u] +
+                     (static_cast<uint32_t>(quarter * 32) << 16);
+        }
+        const bool last = pi == np - 1;
+        if (has_res) {
+          cp_async_wait_all();
           __syncwarp();
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(taddr + h * 32, v);
-          int4 rv[2] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
-          if (has_res) {
-            rv[0] = *reinterpret_cast<const int4*>(my_row + h * 32);
-            rv[1] = *reinterpret_cast<const int4*>(my_row + h * 32 + 16);
-          }
-          tmem_ld_wait();
-          if (p.acc_out && valid) {
-            const size_t dpix = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
-            int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix * p.OC + n0 + c0 + h * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_int4((int)v[4 * j], (int)v[4 * j + 1], (int)v[4 * j + 2], (int)v[4 * j + 3]);
-          }
-          const float4* a4 = reinterpret_cast<const float4*>(s_alpha + c0 + h * 32);
-          const float4* b4 = reinterpret_cast<const float4*>(s_beta + c0 + h * 32);
-          const uint32_t* rw = reinterpret_cast<const uint32_t*>(rv);
-          uint32_t packed[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 al = a4[j], be = b4[j];
-            float t0 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 0])), al.x, be.x);
-            float t1 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 1])), al.y, be.y);
-            float t2 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 2])), al.z, be.z);
-            float t3 = __fmaf_rn(static_cast<float>(static_cast<int32_t>(v[4 * j + 3])), al.w, be.w);
-            if (has_res) {
-              const uint32_t w = rw[j];
-              t0 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w)), res_mul, t0);
-              t1 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 8)), res_mul, t1);
-              t2 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 16)), res_mul, t2);
-              t3 = __fmaf_rn(static_cast<float>(static_cast<int8_t>(w >> 24)), res_mul, t3);
-            }
-            const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2),
-                                             __float2int_rn(t3));
-            packed[j] = __vmaxs4(q, relu_floor);
-          }
-          *reinterpret_cast<int4*>(my_row + h * 32) = make_int4((int)packed[0], (int)packed[1], (int)packed[2], (int)packed[3]);
-          *reinterpret_cast<int4*>(my_row + h * 32 + 16) =
-              make_int4((int)packed[4], (int)packed[5], (int)packed[6], (int)packed[7]);
+#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC>(p, e, taddr, c0, g_own, last, &acc_empty[cs])
+#define DLQ_EPI_SHAPES(RES)                                       \
+  do {                                                            \
+    if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \
+    else if (c0[0] == c0[1]) DLQ_EPI(RES, 2, true, false);        \
+    else DLQ_EPI(RES, 2, false, false);                           \
+  } while (0)
+        if (p.acc_out) { if (has_res) DLQ_EPI(true, 1, true, true); else DLQ_EPI(false, 1, true, true); }
+        else if (has_res) DLQ_EPI_SHAPES(true);
+        else DLQ_EPI_SHAPES(false);
+#undef DLQ_EPI_SHAPES
+#undef DLQ_EPI
+        if (has_res) {
+          if (pi + 1 < n_pairs) prefetch_pair(st, pi + 1);
+          else if (st + static_cast<int>(gridDim.x) < st_end) prefetch_pair(st + gridDim.x, 0);
         }
-        __syncwarp();
-        if (p.out) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int srow = 8 * j + crow;
-            const uint32_t op = __shfl_sync(0xffffffffu, opix, srow);
-            if (op != kInvalid) {
-              const int4 v = *reinterpret_cast<const int4*>(stage + srow * kEpiStageRow + cq * 16);
-              *(reinterpret_cast<int4*>(p.out + static_cast<size_t>(op) * p.OC + n0 + c0) + cq) = v;
-            }
-          }
-        }
-        __syncwarp();
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[cs]);
+      if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[cs]);
+      }
       if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
+    if (has_res) cp_async_wait_all();
     if (p.dbg_times && ew == 0 && lane == 0) {
       long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
       d[4] = clock64() - t_begin; d[5] = t_wait;

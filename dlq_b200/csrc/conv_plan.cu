@@ -252,7 +252,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   }
 
   // ---- tile shape: MT tiles of 128 positions per super-tile, two TMEM accumulator stages when they fit
-  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 3072 /*alpha,beta,barriers*/ - 8 * kEpiStageBytes;
+  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 3072 /*alpha,beta,barriers*/ - 16 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
   if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) MT = v; }
@@ -286,6 +286,13 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.acc_stages = (2 * MT * p.n_tile <= 512) ? 2 : 1;
   const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
   p.num_super = static_cast<int>((total_pos + MT * kTileM - 1) / (MT * kTileM));
+  // epilogue position decode by multiply-high instead of division: exact while positions < 2^24 and divisors <= 256
+  // (floor(2^32/d)+1; the kernel falls back to hardware division when the magics are 0)
+  p.wp_magic = p.pv_magic = 0;
+  if (total_pos + 2LL * MT * kTileM * ctx->num_sms < (1LL << 24) && p.Wp >= 2 && p.Wp <= 256 && p.Pv >= 2 && p.Pv <= 256) {
+    p.wp_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Wp)) + 1u;
+    p.pv_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Pv)) + 1u;
+  }
 
   // ---- epilogue
   p.alpha = alpha;
@@ -348,7 +355,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   L->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_tiles), 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
-            2 * sizeof(float) * p.n_tile + 8 * kEpiStageBytes + 2 * (kMaxSteps + 8) + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
+            2 * sizeof(float) * p.n_tile + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
   return DLQ_OK;
 }
 
