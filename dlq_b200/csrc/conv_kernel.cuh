@@ -19,9 +19,18 @@
 //   so one K=32 MMA covers two horizontally adjacent taps.
 //   (All three addressing tricks are validated by probe/umma_probe.cu on a B200.)
 //
-// Warp roles (256 or 384 threads): warp 0 = activation-patch TMA producer, warp 1 = MMA issuer
-//   (+TMEM alloc), warp 2 = weight-step bulk-copy producer, warp 3 = spare, warps 4.. = epilogue
-//   (4 or 8 warps): tcgen05.ld -> alpha/beta/residual/ReLU/requant -> 16-byte stores.
+// CTA pairs (template TWO): for output-channel tiles of 128 the kernel runs as clusters of two CTAs on the two SMs
+//   of a TPC and issues tcgen05.mma.cta_group::2 (M = 256): each SM feeds its own 128 positions and HALF of the
+//   weight rows from its own shared memory, which halves the shared-memory operand traffic per MAC - the
+//   resource that bounds the single-CTA form (probe/mma_rate.cu: one SS MMA reads 4 KB + 32 N bytes per N/2
+//   cycles of tensor time against 128 B/clk of shared-memory bandwidth).  Pairs use row-aligned super-tiles (a
+//   whole number of virtual rows) so both CTAs address their patches with identical descriptors.
+//
+// Warp roles (384 threads): warp 0 = activation-patch TMA producer, warps 1 and 3 = MMA issuers (warp 1 owns
+//   TMEM), warp 2 = weight-step TMA producer, warps 4..11 = epilogue: tcgen05.ld -> alpha/beta/residual/ReLU/
+//   requant -> staged 16-byte stores.  In a pair only the rank-0 CTA issues MMAs; "full" barriers live in the
+//   rank-0 CTA (both producers arrive on them), "empty"/"accumulator full" barriers are signalled in both CTAs
+//   by a multicast tcgen05.commit.
 // Pipelines: A patch ring (a_full/a_empty), weight-step ring (b_full/b_empty), TMEM accumulator
 //   stages (acc_full/acc_empty).
 #pragma once
@@ -40,13 +49,20 @@ __device__ __forceinline__ int epi_stage_off(int row, int chunk) {
   return row * kEpiStageRow + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
+
 struct ConvKernelParams {
   // virtual output space
   int Wp, Wo, Ho, Pv, N;
-  int num_super;          // number of super-tiles (each MT*128 positions)
-  int MT;                 // M tiles per super-tile
-  int n_tile;             // UMMA N (output channels per CTA column)
+  int total_pos;          // N * Pv * Wp
+  int num_super;          // number of super-tiles
+  int super_stride;       // positions a super-tile owns (distance between consecutive super-tile origins):
+                          // MT*128, or a whole number of virtual rows (<= MT*128) for CTA pairs
+  int MT;                 // M tiles (128 positions) per super-tile
+  int n_tile;             // UMMA N (output channels per work item)
+  int n_tiles;            // OC / n_tile
   int OC;                 // total output channels
+  int two;                // 1: CTA pairs (cta_group::2); a pair works on super-tiles 2*sp and 2*sp+1 together
+  int n_items;            // work items = (super-tile or super-tile pair) x n-tile, dealt round-robin to CTAs / pairs
   // A patch: n_sub sub-patches (parity plane x channel block); each is ONE 3-D TMA load and one
   // stage of the A ring.  K steps are grouped by sub-patch: sub s owns steps [sub_step0[s], sub_step0[s+1]).
   int n_sub;
@@ -61,12 +77,9 @@ struct ConvKernelParams {
   int n_steps;
   uint16_t step_a16[kMaxSteps];   // A view offset of each step inside its sub-patch, in 16-byte units (tap shift * ROWB / 16)
   int a_stages, b_stages, acc_stages;
-  int b_resident;         // 1: all weight steps stay in smem (b_stages == n_steps), loaded once per CTA
-  int cluster;            // CTAs per cluster along grid.x (1, 2 or 4): weight steps are fetched once per cluster
-                          // (each CTA loads 1/cluster of a step and multicasts it)
-  int trips;              // super-tiles per CTA (uniform; trailing ones may be past num_super = all-garbage)
-  uint32_t step_bytes;    // weight image bytes per step (n_tile * ROWB, or n_tile*32 for the stem)
-  const uint8_t* wimg;    // [n_tiles][n_steps][step_bytes] pre-swizzled smem images
+  int b_resident;         // 1: all weight steps stay in smem (b_stages == n_steps), loaded once per CTA (needs n_tiles == 1)
+  int w_rows;             // weight rows (output channels) each CTA loads per step: n_tile, or n_tile/2 in a pair
+  uint32_t step_bytes;    // w_rows * ROWB
   // epilogue:  y = clamp(rne(fmaf(r, res_mul, fmaf(acc, alpha[oc], beta[oc]))), lo, 127)
   const float* alpha;     // [OC] requantisation multiplier (output scale folded in)
   const float* beta;      // [OC]
@@ -78,8 +91,8 @@ struct ConvKernelParams {
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
   uint32_t wp_magic, pv_magic;   // floor(2^32/d)+1 for d = Wp, Pv (exact for positions < 2^24); 0 = use hardware division
-  int dbg;                // tuning experiments only: 1 = skip TMEM loads, 2 = skip MMA issue, 4 = skip A loads
-  long long* dbg_times;   // optional [gridDim.x*gridDim.y][8] cycle counters (tuning): see conv_plan.cu
+  int dbg;                // tuning experiments only: 1 = skip the epilogue, 2 = skip MMA issue, 4 = skip A loads
+  long long* dbg_times;   // optional [gridDim.x][8] cycle counters (tuning): see conv_plan.cu
 };
 
 __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
@@ -91,64 +104,71 @@ __device__ __forceinline__ uint32_t pack_sat_s8x4(int a, int b, int c, int d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// MMA issuer (one elected lane of an issuing warp).  tcgen05.mma issue is the critical path of the whole
-// kernel: the tensor pipe does not queue ahead, so every cycle the issuing lane spends between two MMAs is
-// a cycle the pipe idles (probe/mma_rate.cu).  Hence: everything a compile-time offset from (a_lo, b_lo,
-// d0), constant accumulate flags (first step peeled), no data-dependent branch or multiply in the step
-// body, and separate instantiations for resident / streamed weights and 1 / 2 tiles per issuer.
+// MMA issuer (one elected lane of an issuing warp).  Everything is a compile-time offset from (a_lo, b_lo, d0),
+// the accumulate flag is constant (first step peeled) and nothing data-dependent sits between two tcgen05.mma:
+// a branch or an address multiply there costs ~25 cycles of tensor-pipe idle time (probe/mma_rate.cu "morph").
 // ------------------------------------------------------------------------------------------------
 struct IssuerCtx {
-  uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *acc_empty;
+  uint64_t *a_full, *a_empty, *b_full, *b_empty, *acc_full, *acc_empty, *k_first;
   const uint16_t* step_a16;     // shared-memory copy of the per-step A offsets
   const int16_t* sub_step0;
   uint32_t sA_u32, sB_u32, a_stage16, b_stage16;   // ring bases (shared window) and stage sizes in 16-byte units
   uint32_t tmem_base, acc_cols, n_tile;
-  int n_sub, a_stages, b_stages, acc_stages, cluster, Wp, super_pos;
-  int st_begin, st_end, st_stride;
+  int n_sub, a_stages, b_stages, acc_stages, Wp, super_stride, n_tiles;
+  int it_begin, it_end, it_stride;
   uint32_t tile_off16;          // this issuer's first tile, in 16-byte units down the patch
   uint32_t d_off;               // this issuer's first accumulator column offset
   bool leader;
   int dbg;
 };
 
-template <int ROWB, int MYMT, bool FIRST>
+template <bool TWO>
+__device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (TWO) umma_i8_pair(d, a, b, idesc, acc); else umma_i8(d, a, b, idesc, acc);
+}
+template <bool TWO>
+__device__ __forceinline__ void umma_done(uint64_t* bar) {
+  if (TWO) umma_commit_pair(bar); else umma_commit(bar);
+}
+
+// KSEL: 0 = every K=32 slice of the step, 1 / 2 = first / second half of them (two issuers sharing ONE accumulator)
+template <int ROWB, int MYMT, bool FIRST, bool TWO, int KSEL>
 __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_t a_lo, uint32_t b_lo, uint32_t d0,
                                            uint32_t n_tile, uint32_t idesc) {
   constexpr int K32 = ROWB / 32;
+  constexpr int KK0 = KSEL == 2 ? K32 / 2 : 0;
+  constexpr int KK1 = KSEL == 1 ? K32 / 2 : K32;
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;
 #pragma unroll
-  for (int kk = 0; kk < K32; ++kk) {
+  for (int kk = KK0; kk < KK1; ++kk) {
 #pragma unroll
     for (int mt = 0; mt < MYMT; ++mt) {   // tile inner: consecutive MMAs hit different accumulators
-      umma_i8(d0 + (mt ? n_tile : 0u), (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),
-              (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc,
-              (FIRST && kk == 0) ? 0u : 1u);
+      umma_issue<TWO>(d0 + (mt ? n_tile : 0u), (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),
+                      (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc, (FIRST && kk == KK0) ? 0u : 1u);
     }
   }
 }
 
-template <int ROWB, int MYMT, bool RESIDENT>
+template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL>
 __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out) {
   constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
-  constexpr uint32_t A_SBO = 8u * ROWB;
-  constexpr uint32_t A_LBO = 0u;
-  constexpr uint32_t B_SBO = 8u * ROWB;
-  const uint32_t idesc = umma_idesc_s8(kTileM, c.n_tile);
-  const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT) >> 32);
-  const uint32_t b_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, B_SBO, LAYOUT) >> 32);
-  const uint32_t a_flags = static_cast<uint32_t>(umma_smem_desc(0, A_LBO, A_SBO, LAYOUT)) + (c.sA_u32 >> 4) + c.tile_off16;
-  const uint32_t b_flags =
-      static_cast<uint32_t>(umma_smem_desc(0, 0u, B_SBO, LAYOUT)) + (c.sB_u32 >> 4);
-  const uint16_t cta_mask = static_cast<uint16_t>((1u << c.cluster) - 1u);
+  constexpr uint32_t SBO = 8u * ROWB;
+  const uint32_t idesc = umma_idesc_s8(TWO ? 2 * kTileM : kTileM, c.n_tile);
+  const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT) >> 32);
+  const uint32_t b_hi = a_hi;
+  const uint32_t a_flags = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT)) + (c.sA_u32 >> 4) + c.tile_off16;
+  const uint32_t b_flags = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT)) + (c.sB_u32 >> 4);
   uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
   long long t_acc = 0, t_a = 0, t_b = 0;
   bool first_pass = true;
-  for (int st = c.st_begin; st < c.st_end; st += c.st_stride) {
-    const int g0 = st * c.super_pos;
+  for (int it = c.it_begin; it < c.it_end; it += c.it_stride) {
+    const int sp = it / c.n_tiles;
+    const int g0 = (TWO ? 2 * sp : sp) * c.super_stride;          // (pairs: super_stride % Wp == 0, so in_patch == 0)
     const uint32_t in_patch16 = static_cast<uint32_t>(g0 - (g0 / c.Wp) * c.Wp) * (ROWB / 16);
     long long tw = clock64();
-    mbar_wait(&c.acc_empty[cs], cph ^ 1u);
+    if (TWO) mbar_wait_cluster(&c.acc_empty[cs], cph ^ 1u); else mbar_wait(&c.acc_empty[cs], cph ^ 1u);
     t_acc += clock64() - tw;
+    tc_fence_after();
     const uint32_t d0 = c.tmem_base + cs * c.acc_cols + c.d_off;
     for (int s = 0; s < c.n_sub; ++s) {
       tw = clock64();
@@ -166,7 +186,7 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         tc_fence_after();
       }
-      if (s == 0) {                               // peeled first step of the super-tile: overwrites the accumulators
+      if (s == 0) {                               // peeled first step of the item: overwrites the accumulators
         if (!RESIDENT) {
           tw = clock64();
           mbar_wait(&c.b_full[bs], bph);
@@ -175,11 +195,11 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, true>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
-          if (!RESIDENT) {
-            if (c.cluster > 1) umma_commit_multicast(&c.b_empty[bs], cta_mask);
-            else umma_commit(&c.b_empty[bs]);
-          }
+          // K-split: the second issuer only accumulates, and only after the first one has issued the overwriting MMA
+          if (KSEL == 2) mbar_wait(&c.k_first[cs], cph);
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (KSEL == 1) mbar_arrive(&c.k_first[cs]);
+          if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
         ++k;
@@ -193,18 +213,17 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
-          if (!RESIDENT) {
-            if (c.cluster > 1) umma_commit_multicast(&c.b_empty[bs], cta_mask);
-            else umma_commit(&c.b_empty[bs]);
-          }
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false, TWO, KSEL>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
       }
-      if (c.leader) umma_commit(&c.a_empty[as]);     // sub-patch stage free
+      if (c.dbg & 8) { tw = clock64(); }
+      if (c.leader) umma_done<TWO>(&c.a_empty[as]);     // sub-patch stage free
+      if (c.dbg & 8) { __syncwarp(); t_b += clock64() - tw; }
       if (++as == static_cast<uint32_t>(c.a_stages)) { as = 0; aph ^= 1u; }
     }
-    if (c.leader) umma_commit(&c.acc_full[cs]);      // accumulators ready for the epilogue
+    if (c.leader) umma_done<TWO>(&c.acc_full[cs]);      // accumulators ready for the epilogue
     __syncwarp();
     first_pass = false;
     if (++cs == static_cast<uint32_t>(c.acc_stages)) { cs = 0; cph ^= 1u; }
@@ -277,7 +296,7 @@ __device__ __forceinline__ void fma2_rn(float& d0, float& d1, float a0, float a1
 template <bool HAS_RES, int NU, bool SAME_CB, bool ACC_OUT = false>
 __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCtx& e, const uint32_t (&taddr)[2],
                                           const int (&c0)[2], const int (&g_own)[2], bool release_acc,
-                                          uint64_t* acc_empty_bar) {
+                                          uint32_t acc_empty_addr) {
   uint32_t opix[NU];
   size_t dpix[NU];
   bool valid[NU];
@@ -309,7 +328,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
     if (release_acc && h == 1) {      // accumulators are in registers: hand the TMEM stage back to the MMA warps
       tc_fence_before();
       __syncwarp();
-      if (e.lane == 0) mbar_arrive(acc_empty_bar);
+      if (e.lane == 0) mbar_arrive_cluster(acc_empty_addr);     // (rank-0 CTA's barrier when running as a pair)
     }
     if (ACC_OUT) {                    // raw accumulators (parity / debug entry points only)
 #pragma unroll
@@ -389,17 +408,11 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
 }
 
 // smem layout (dynamic, 1024-aligned base):
-//   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha,beta: 2*n_tile f32]
+//   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha, beta: 2*OC f32]
 //   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
-template <int ROWB>
+template <int ROWB, bool TWO>
 __global__ void __launch_bounds__(384, 1)
-conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p) {
-  constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
-  // descriptor strides: swizzled K-major rows of ROWB bytes, SBO = 8 rows
-  constexpr uint32_t A_SBO = 8u * ROWB;
-  constexpr uint32_t A_LBO = 0u;
-  constexpr uint32_t B_SBO = 8u * ROWB;
-  constexpr int K32 = ROWB / 32;      // MMAs (K = 32) per step per tile
+conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmw, const ConvKernelParams p) {
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   extern __shared__ uint8_t smem_raw[];
@@ -411,8 +424,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   uint8_t* sA = smem;
   uint8_t* sB = sA + static_cast<size_t>(p.a_stages) * a_stage_bytes;
   float* s_alpha = reinterpret_cast<float*>(sB + static_cast<size_t>(p.b_stages) * b_stage_bytes);
-  float* s_beta = s_alpha + p.n_tile;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.n_tile);          // [epilogue warps][kEpiStageBytes]
+  float* s_beta = s_alpha + p.OC;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.OC);              // [epilogue warps][2 slots][kEpiStageBytes]
   uint16_t* s_step_a16 = reinterpret_cast<uint16_t*>(s_stage + 16 * kEpiStageBytes);   // [kMaxSteps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_step_a16 + kMaxSteps + 8);
   uint64_t* a_full = bars;
@@ -421,42 +434,54 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
   uint64_t* b_empty = b_full + p.b_stages;
   uint64_t* acc_full = b_empty + p.b_stages;
   uint64_t* acc_empty = acc_full + p.acc_stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + p.acc_stages);
+  uint64_t* k_first = acc_empty + p.acc_stages;       // K-split handshake, one per accumulator stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_first + p.acc_stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_epi_warps = (blockDim.x >> 5) - 4;
-  // Two MMA-issuing warps (1 and 3) split the M tiles of a super-tile: one issuer cannot keep the tensor pipe
-  // busy (loop / barrier overhead between tcgen05.mma is exposed), two interleaved issuers can.
-  const int n_issuers = p.MT >= 2 ? 2 : 1;
-  const int n_blk = blockIdx.y;                 // output-channel tile
-  const int n0 = n_blk * p.n_tile;
+  // Two MMA-issuing warps (1 and 3): a single one cannot keep the tensor pipe fed (the per-step barrier wait and
+  // descriptor arithmetic are exposed, probe/mma_rate.cu "pattern").  They split the M tiles of a super-tile when
+  // there are at least two, else the K=32 slices of every step (same accumulator; integer accumulation commutes,
+  // the overwriting first MMA is ordered by a handshake).
+  constexpr int K32 = ROWB / 32;
+  const bool k_split = p.MT == 1 && K32 >= 2;
+  const int n_issuers = (p.MT >= 2 || k_split) ? 2 : 1;
+  const int ncta = TWO ? 2 : 1;
+  const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+  const int gid = static_cast<int>(blockIdx.x) / ncta;          // CTA (or pair) index
+  const int G = static_cast<int>(gridDim.x) / ncta;             // CTAs (or pairs) in the grid
   const uint32_t acc_cols = static_cast<uint32_t>(p.MT) * p.n_tile;   // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
   while (tmem_cols < acc_cols * p.acc_stages) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
+    // "full" barriers: one arrive (+ the transaction bytes of every CTA of the pair); "empty" / acc_full ones one
+    // commit per issuer; acc_empty one arrive per epilogue warp of every CTA of the pair
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
-    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.cluster * n_issuers); }
-    for (int i = 0; i < p.acc_stages; ++i) { mbar_init(&acc_full[i], n_issuers); mbar_init(&acc_empty[i], n_epi_warps); }
+    for (int i = 0; i < p.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_issuers); }
+    for (int i = 0; i < p.acc_stages; ++i) {
+      mbar_init(&acc_full[i], n_issuers);
+      mbar_init(&acc_empty[i], n_epi_warps * ncta);
+      mbar_init(&k_first[i], 1);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&tm0);
+    tma_prefetch_desc(&tmw);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (TWO) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < p.n_steps; i += blockDim.x) s_step_a16[i] = p.step_a16[i];
-  for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) {
-    s_alpha[i] = p.alpha ? p.alpha[n0 + i] : 1.f;
-    s_beta[i] = p.beta ? p.beta[n0 + i] : 0.f;
+  for (int i = threadIdx.x; i < p.OC; i += blockDim.x) {
+    s_alpha[i] = p.alpha ? p.alpha[i] : 1.f;
+    s_beta[i] = p.beta ? p.beta[i] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts into them
+  if (TWO) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int super_pos = p.MT * kTileM;
-  const int st_end = static_cast<int>(blockIdx.x) + p.trips * static_cast<int>(gridDim.x);
 
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
@@ -464,78 +489,94 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
       uint32_t as = 0, aph = 0;
       long long t_wait = 0;
       const long long t_begin = clock64();
-      for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
-        const int v0 = (st * super_pos) / p.Wp;
+      for (int it = gid; it < p.n_items; it += G) {
+        const int sp = it / p.n_tiles;
+        const int st = TWO ? 2 * sp + rank : sp;
+        const int v0 = (st * p.super_stride) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
           const long long tw = clock64();
           mbar_wait(&a_empty[as], aph ^ 1u);
           t_wait += clock64() - tw;
+          uint8_t* dst = sA + static_cast<size_t>(as) * a_stage_bytes;
           if (p.dbg & 4) {
-            mbar_arrive(&a_full[as]);
+            if (rank == 0) mbar_arrive(&a_full[as]);
+          } else if (TWO) {
+            // the rank-0 producer alone arrives, expecting BOTH CTAs' bytes; the peer's TMA completes its
+            // transaction bytes on the rank-0 barrier (a remote arrive per load would cost a cluster round trip)
+            if (rank == 0) mbar_expect_tx(&a_full[as], 2u * static_cast<uint32_t>(p.tma_bytes));
+            tma_load_3d_pair(dst, &tm0, leader_cta_addr(&a_full[as]), p.sub_c0[s], p.sub_col0[s],
+                             p.row_mul * v0 + p.sub_row_off[s]);
           } else {
             mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
-            tma_load_3d(sA + static_cast<size_t>(as) * a_stage_bytes, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
-                        p.row_mul * v0 + p.sub_row_off[s]);
+            tma_load_3d(dst, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s], p.row_mul * v0 + p.sub_row_off[s]);
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }
       }
       if (p.dbg_times) {
-        long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+        long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
         d[6] = clock64() - t_begin; d[7] = t_wait;
       }
     }
   } else if (warp == 2) {
     // ===================================================================== B (weight step) producer
+    // weight image rows: [(n-tile * n_steps + step) * n_tile + channel], ROWB bytes each (pre-swizzled); a CTA of a
+    // pair loads its half of the channels
     if (elect_one()) {
       uint32_t bs = 0, bph = 0;
-      const uint8_t* wsrc = p.wimg + static_cast<size_t>(n_blk) * p.n_steps * p.step_bytes;
-      for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
-        if (p.b_resident && st != static_cast<int>(blockIdx.x)) break;   // resident weights: loaded once
+      bool first = true;
+      for (int it = gid; it < p.n_items; it += G) {
+        if (p.b_resident && !first) break;   // resident weights: loaded once
+        first = false;
+        const int sp = it / p.n_tiles;
+        const int nt = it - sp * p.n_tiles;
         for (int k = 0; k < p.n_steps; ++k) {
           mbar_wait(&b_empty[bs], bph ^ 1u);
-          mbar_expect_tx(&b_full[bs], p.step_bytes);
-          if (p.cluster > 1) {
-            const uint32_t slice = p.step_bytes / static_cast<uint32_t>(p.cluster);
-            const uint32_t off = cluster_ctarank() * slice;
-            bulk_g2s_multicast(sB + static_cast<size_t>(bs) * b_stage_bytes + off,
-                               wsrc + static_cast<size_t>(k) * p.step_bytes + off, slice, &b_full[bs],
-                               static_cast<uint16_t>((1u << p.cluster) - 1u));
+          uint8_t* dst = sB + static_cast<size_t>(bs) * b_stage_bytes;
+          const int row0 = (nt * p.n_steps + k) * p.n_tile + rank * p.w_rows;
+          if (TWO) {
+            if (rank == 0) mbar_expect_tx(&b_full[bs], 2u * p.step_bytes);
+            tma_load_2d_pair(dst, &tmw, leader_cta_addr(&b_full[bs]), 0, row0);
           } else {
-            bulk_g2s(sB + static_cast<size_t>(bs) * b_stage_bytes, wsrc + static_cast<size_t>(k) * p.step_bytes,
-                     p.step_bytes, &b_full[bs]);
+            mbar_expect_tx(&b_full[bs], p.step_bytes);
+            tma_load_2d(dst, &tmw, &b_full[bs], 0, row0);
           }
           if (++bs == static_cast<uint32_t>(p.b_stages)) { bs = 0; bph ^= 1u; }
         }
       }
     }
-  } else if (warp == 1 || (warp == 3 && n_issuers == 2)) {
-    // ===================================================================== MMA issuers
+  } else if ((warp == 1 || (warp == 3 && n_issuers == 2)) && rank == 0) {
+    // ===================================================================== MMA issuers (rank-0 CTA of a pair only)
     // The whole warp walks the loop (so the address arithmetic stays warp-uniform); one elected lane
     // issues.  Descriptors are advanced by adding to their low word (start address >> 4).
     IssuerCtx c;
     c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.acc_full = acc_full; c.acc_empty = acc_empty;
+    c.k_first = k_first;
     c.step_a16 = s_step_a16; c.sub_step0 = p.sub_step0;
     c.sA_u32 = smem_u32(sA); c.sB_u32 = smem_u32(sB); c.a_stage16 = a_stage_bytes >> 4; c.b_stage16 = b_stage_bytes >> 4;
     c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.n_tile = static_cast<uint32_t>(p.n_tile);
-    c.n_sub = p.n_sub; c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.acc_stages = p.acc_stages; c.cluster = p.cluster;
-    c.Wp = p.Wp; c.super_pos = super_pos;
-    c.st_begin = static_cast<int>(blockIdx.x); c.st_end = st_end; c.st_stride = static_cast<int>(gridDim.x);
+    c.n_sub = p.n_sub; c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.acc_stages = p.acc_stages;
+    c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles;
+    c.it_begin = gid; c.it_end = p.n_items; c.it_stride = G;
     const int issuer = (warp == 1) ? 0 : 1;
-    const int my_mt = p.MT / n_issuers;                 // tiles this issuer owns: [issuer*my_mt, +my_mt)
-    c.tile_off16 = static_cast<uint32_t>(issuer * my_mt) * TILE16;
-    c.d_off = static_cast<uint32_t>(issuer * my_mt) * static_cast<uint32_t>(p.n_tile);
+    const int my_mt = k_split ? 1 : p.MT / n_issuers;   // tiles this issuer owns: [issuer*my_mt, +my_mt)
+    c.tile_off16 = k_split ? 0u : static_cast<uint32_t>(issuer * my_mt) * TILE16;
+    c.d_off = k_split ? 0u : static_cast<uint32_t>(issuer * my_mt) * static_cast<uint32_t>(p.n_tile);
     c.leader = elect_one();
     c.dbg = p.dbg;
     long long tt[3] = {0, 0, 0};
     const long long t_begin = clock64();
-    if (p.b_resident) {
-      if (my_mt == 2) run_issuer<ROWB, 2, true>(c, tt); else run_issuer<ROWB, 1, true>(c, tt);
+    if (k_split) {
+      constexpr int KA = K32 >= 2 ? 1 : 0, KB = K32 >= 2 ? 2 : 0;   // (K32 == 1 never takes this branch)
+      if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB>(c, tt); }
+      else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB>(c, tt); }
+    } else if (p.b_resident) {
+      if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0>(c, tt);
     } else {
-      if (my_mt == 2) run_issuer<ROWB, 2, false>(c, tt); else run_issuer<ROWB, 1, false>(c, tt);
+      if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0>(c, tt);
     }
     if (p.dbg_times && c.leader && issuer == 0) {
-      long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
       d[0] = clock64() - t_begin; d[1] = tt[0]; d[2] = tt[1]; d[3] = tt[2];
     }
   } else if (warp >= 4) {
@@ -549,24 +590,34 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     const bool has_res = p.residual != nullptr;
     const int cblocks = p.n_tile >> 6;
     const int n_units = p.MT * cblocks;
-    const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per super-tile: grp, grp + n_groups, ...
+    const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per item: grp, grp + n_groups, ...
     const int upp = p.acc_out ? 1 : 2;                  // units per pass (raw-accumulator output: one at a time)
     const int n_pairs = (upw + upp - 1) / upp;
     EpiCtx e;
     e.s_alpha = s_alpha; e.s_beta = s_beta;
     e.slots = s_stage + ew * 2 * kEpiStageBytes;
     e.lane = lane; e.crow = lane >> 2; e.cq = lane & 3;
-    e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = n0;
+    e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = 0;
     e.relu_mask = p.relu ? 0xFFFFFFFFu : 0u;
     e.res_mul = p.res_mul;
-    auto prefetch_pair = [&](int st, int pi) {
+    // global position of this lane's row in tile mt of super-tile st (rows past the super-tile's own positions
+    // belong to the next super-tile: mapped to total_pos, which decodes as image N = invalid)
+    auto own_pos = [&](int st, int mt) {
+      const int local = mt * kTileM + row;
+      return local < p.super_stride ? st * p.super_stride + local : p.total_pos;
+    };
+    auto prefetch_pair = [&](int it, int pi) {
+      const int sp = it / p.n_tiles;
+      const int nt = it - sp * p.n_tiles;
+      const int st = TWO ? 2 * sp + rank : sp;
+      e.n0 = nt * p.n_tile;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int k = upp * pi + u;
         if (u < upp && k < upw) {
           const int unit = grp + k * n_groups;
           const int mt = unit / cblocks, cb = unit - mt * cblocks;
-          epi_prefetch_res(p, e, u, st * super_pos + mt * kTileM + row, cb << 6);
+          epi_prefetch_res(p, e, u, own_pos(st, mt), cb << 6);
         }
       }
       cp_async_commit();
@@ -574,8 +625,12 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
     uint32_t cs = 0, cph = 0;
     long long t_wait = 0;
     const long long t_begin = clock64();
-    if (has_res && static_cast<int>(blockIdx.x) < st_end && n_pairs > 0) prefetch_pair(blockIdx.x, 0);
-    for (int st = blockIdx.x; st < st_end; st += gridDim.x) {
+    if (has_res && gid < p.n_items && n_pairs > 0) prefetch_pair(gid, 0);
+    for (int it = gid; it < p.n_items; it += G) {
+      const int sp = it / p.n_tiles;
+      const int nt = it - sp * p.n_tiles;
+      const int st = TWO ? 2 * sp + rank : sp;
+      const uint32_t acc_empty_addr = TWO ? leader_cta_addr(&acc_empty[cs]) : smem_u32(&acc_empty[cs]);
       const long long tw = clock64();
       mbar_wait(&acc_full[cs], cph);
       t_wait += clock64() - tw;
@@ -585,12 +640,15 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
         uint32_t taddr[2];
         int c0[2], g_own[2];
         const int nu = (2 * pi + 1 < upw && !p.acc_out) ? 2 : 1;
+        e.n0 = nt * p.n_tile;
+        e.s_alpha = s_alpha + e.n0;
+        e.s_beta = s_beta + e.n0;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
           const int mt = unit / cblocks, cb = unit - mt * cblocks;
           c0[u] = cb << 6;
-          g_own[u] = st * super_pos + mt * kTileM + row;
+          g_own[u] = own_pos(st, mt);
           taddr[u] = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile + c0[u] +
                      (static_cast<uint32_t>(quarter * 32) << 16);
         }
@@ -599,7 +657,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
           cp_async_wait_all();
           __syncwarp();
         }
-#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC>(p, e, taddr, c0, g_own, last, &acc_empty[cs])
+#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC>(p, e, taddr, c0, g_own, last, acc_empty_addr)
 #define DLQ_EPI_SHAPES(RES)                                       \
   do {                                                            \
     if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \
@@ -612,27 +670,29 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const ConvKernelParams p
 #undef DLQ_EPI_SHAPES
 #undef DLQ_EPI
         if (has_res) {
-          if (pi + 1 < n_pairs) prefetch_pair(st, pi + 1);
-          else if (st + static_cast<int>(gridDim.x) < st_end) prefetch_pair(st + gridDim.x, 0);
+          if (pi + 1 < n_pairs) prefetch_pair(it, pi + 1);
+          else if (it + G < p.n_items) prefetch_pair(it + G, 0);
         }
       }
       if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[cs]);
+        if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
       }
       if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
     }
     if (has_res) cp_async_wait_all();
     if (p.dbg_times && ew == 0 && lane == 0) {
-      long long* d = p.dbg_times + (static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
       d[4] = clock64() - t_begin; d[5] = t_wait;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster > 1) cluster_sync_all();   // nobody leaves while a peer may still write its smem / barriers
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (TWO) cluster_sync_all();   // nobody leaves while the peer may still arrive on its barriers / read its smem
+  if (warp == 1) {
+    if (TWO) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
+  }
 }
 
 }  // namespace dlq

@@ -135,8 +135,9 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
       DLQ_ARG(ctx, false, "unsupported (kernel, stride, pad) combination");
     }
   }
-  // tcgen05.mma (SS, M=128, K=32) costs ~42 + N/2 cycles (probe/mma_rate.cu): the widest N amortises the A fetch
-  out->n_tile = (OC % 256 == 0) ? 256 : (OC % 128 == 0) ? 128 : 64;
+  // 128-channel tiles run as CTA pairs (cta_group::2, M = 256): per SM an MMA then reads 4 KB of A + 2 KB of B per
+  // 64 tensor cycles, inside the 128 B/clk shared-memory budget; 64-channel layers stay single-CTA
+  out->n_tile = (OC % 128 == 0) ? 128 : 64;
   if (const char* e = getenv("DLQ_DBG_NTILE")) { const int v = atoi(e); if (v >= 64 && OC % v == 0) out->n_tile = v; }
   std::vector<SubDesc> subs;
   std::vector<StepDesc> steps;
@@ -229,8 +230,6 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   make_schedule(w, subs, steps);
   p.n_sub = static_cast<int>(subs.size());
   p.n_steps = static_cast<int>(steps.size());
-  p.step_bytes = w->step_bytes;
-  p.wimg = w->d_img;
   int maxshift = 0;
   for (int k = 0; k < p.n_steps; ++k) {
     const int sh = steps[k].da * p.Wp + steps[k].db;
@@ -251,19 +250,28 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     p.sub_step0[p.n_sub] = static_cast<int16_t>(p.n_steps);
   }
 
-  // ---- tile shape: MT tiles of 128 positions per super-tile, two TMEM accumulator stages when they fit
-  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 3072 /*alpha,beta,barriers*/ - 16 * kEpiStageBytes;
+  // ---- tile shape.  CTA pairs: one 128-position tile per CTA, super-tile = a whole number of virtual rows (both
+  // CTAs then view their patches through identical descriptors).  Single CTA: MT tiles per super-tile.
+  const int n_tiles = w->OC / w->n_tile;
+  p.n_tiles = n_tiles;
+  p.two = (w->n_tile == 128 && p.Wp <= kTileM && !getenv("DLQ_DBG_NO_PAIR")) ? 1 : 0;
+  const int ncta = p.two ? 2 : 1;
+  p.w_rows = w->n_tile / ncta;
+  p.step_bytes = static_cast<uint32_t>(p.w_rows) * rowb;
+  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 1024 /*barriers, step table*/ -
+                        8 * static_cast<size_t>(w->OC) /*alpha, beta*/ - 16 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
-  if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) MT = v; }
+  if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * p.n_tile <= 512) MT = v; }
   int NR = 0;
   const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;
   for (;; MT >>= 1) {
-    NR = (p.Wp - 1 + MT * kTileM - 1 + maxshift) / p.Wp + 1;
+    const int in_patch_max = p.two ? 0 : p.Wp - 1;
+    NR = (in_patch_max + MT * kTileM - 1 + maxshift) / p.Wp + 1;
     p.tma_bytes = NR * p.Wp * rowb;
     p.sub_bytes = (p.tma_bytes + 1023) & ~1023;
-    // weights resident in smem when they are small (stem, layer1, stride-2 / 1x1 convs): no per-tile re-fetch
-    p.b_resident = (all_b <= 80 * 1024 && all_b + 2 * static_cast<size_t>(p.sub_bytes) <= budget) ? 1 : 0;
+    // weights resident in smem when they are small (stem, layer1, stride-2 / 1x1 convs): no per-item re-fetch
+    p.b_resident = (n_tiles == 1 && all_b <= 80 * 1024 && all_b + 2 * static_cast<size_t>(p.sub_bytes) <= budget) ? 1 : 0;
     const int min_a = 2;
     if (p.b_resident) {
       p.b_stages = p.n_steps;
@@ -280,16 +288,20 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   // debug / tuning overrides (environment; not used by tests or the benchmark)
   if (const char* e = getenv("DLQ_DBG_A_STAGES")) p.a_stages = atoi(e);
   if (const char* e = getenv("DLQ_DBG_B_STAGES")) { if (!p.b_resident) p.b_stages = atoi(e); }
-  DLQ_ARG(ctx, p.a_stages >= 1 && p.b_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256,
+  DLQ_ARG(ctx, p.a_stages >= 1 && p.b_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256 && w->OC <= 2048,
           "conv patch does not fit shared memory / TMA box");
   p.MT = MT;
   p.acc_stages = (2 * MT * p.n_tile <= 512) ? 2 : 1;
+  p.super_stride = p.two ? ((MT * kTileM) / p.Wp) * p.Wp : MT * kTileM;
   const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
-  p.num_super = static_cast<int>((total_pos + MT * kTileM - 1) / (MT * kTileM));
+  DLQ_ARG(ctx, total_pos + 4LL * MT * kTileM < (1LL << 31), "batch too large for 32-bit position arithmetic");
+  p.total_pos = static_cast<int>(total_pos);
+  p.num_super = static_cast<int>((total_pos + p.super_stride - 1) / p.super_stride);
+  p.n_items = ((p.num_super + ncta - 1) / ncta) * n_tiles;
   // epilogue position decode by multiply-high instead of division: exact while positions < 2^24 and divisors <= 256
   // (floor(2^32/d)+1; the kernel falls back to hardware division when the magics are 0)
   p.wp_magic = p.pv_magic = 0;
-  if (total_pos + 2LL * MT * kTileM * ctx->num_sms < (1LL << 24) && p.Wp >= 2 && p.Wp <= 256 && p.Pv >= 2 && p.Pv <= 256) {
+  if (total_pos + 4LL * MT * kTileM < (1LL << 24) && p.Wp >= 2 && p.Wp <= 256 && p.Pv >= 2 && p.Pv <= 256) {
     p.wp_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Wp)) + 1u;
     p.pv_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Pv)) + 1u;
   }
@@ -338,32 +350,36 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     return DLQ_ERR_CUDA;
   }
 
-  const int n_tiles = w->OC / w->n_tile;
-  int gx = std::min(p.num_super, std::max(1, ctx->num_sms / n_tiles));
-  // streamed weights: CTAs of a cluster share every weight step through multicast (L2 -> SM traffic / cluster)
-  p.cluster = 1;
-  if (!p.b_resident) {
-    // measured on B200 (profiles/r01_mma_rate.log, r01_cluster_sweep.txt): the convs are bound by the MMA
-    // operand fetch, not by L2 -> SM weight traffic, so sharing buys nothing yet; off unless requested
-    int want = 1;
-    if (const char* e = getenv("DLQ_DBG_CLUSTER")) want = std::max(1, atoi(e));
-    while (want > 1 && (gx < want || (p.step_bytes / want) % 16 != 0)) want >>= 1;
-    p.cluster = want;
-    gx = gx / p.cluster * p.cluster;
+  // ---- TMA descriptor over the packed weight image: rows of ROWB bytes (already swizzled), box = one CTA's rows of a step
+  {
+    cuuint64_t wdim[2] = {static_cast<cuuint64_t>(rowb), static_cast<cuuint64_t>(n_tiles) * p.n_steps * w->n_tile};
+    cuuint64_t wstr[1] = {static_cast<cuuint64_t>(rowb)};
+    cuuint32_t wbox[2] = {static_cast<cuuint32_t>(rowb), static_cast<cuuint32_t>(p.w_rows)};
+    cuuint32_t west[2] = {1, 1};
+    const CUresult rw = enc(&L->tmap_w, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, w->d_img, wdim, wstr, wbox, west,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rw != CUDA_SUCCESS) {
+      ctx->err = "cuTensorMapEncodeTiled (weights) failed with CUresult " + std::to_string(static_cast<int>(rw));
+      return DLQ_ERR_CUDA;
+    }
   }
-  p.trips = (p.num_super + gx - 1) / gx;
-  L->grid = dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_tiles), 1);
+
+  // persistent grid: one CTA (or CTA pair) per SM (pair of SMs), work items dealt round-robin
+  const int G = std::max(1, std::min(p.n_items, ctx->num_sms / ncta));
+  L->grid = dim3(static_cast<unsigned>(G * ncta), 1, 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
-            2 * sizeof(float) * p.n_tile + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) + 8 * (2 * p.a_stages + 2 * p.b_stages + 2 * p.acc_stages) + 16;
+            2 * sizeof(float) * w->OC + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) +
+            8 * (2 * p.a_stages + 2 * p.b_stages + 3 * p.acc_stages) + 16;
   return DLQ_OK;
 }
 
-template <int ROWB>
+template <int ROWB, bool TWO>
 static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   static size_t configured[16] = {0};   // per-device max dynamic smem already requested
   if (configured[ctx->device & 15] < L.smem) {
-    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(ctx->smem_optin)));
     configured[ctx->device & 15] = ctx->smem_optin;
   }
@@ -374,32 +390,44 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(L.p.cluster);
+  attr[0].val.clusterDim.x = TWO ? 2u : 1u;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB>, L.tmap, L.p));
+  DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB, TWO>, L.tmap, L.tmap_w, L.p));
   if (L.p.dbg_times) {
     cudaStreamSynchronize(ctx->stream);
-    const int nb = static_cast<int>(L.grid.x * L.grid.y);
+    const int nb = static_cast<int>(L.grid.x);
     std::vector<long long> h(static_cast<size_t>(nb) * 8);
     cudaMemcpy(h.data(), L.p.dbg_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
     double a[8] = {0};
+    int cnt[8] = {0};
     for (int b = 0; b < nb; ++b)
-      for (int j = 0; j < 8; ++j) a[j] += static_cast<double>(h[static_cast<size_t>(b) * 8 + j]) / nb;
-    fprintf(stderr, "[dbg_times] grid %ux%u MT=%d n_tile=%d trips=%d | mma: total %.0f wait_acc %.0f wait_a %.0f wait_b %.0f | "
+      for (int j = 0; j < 8; ++j)
+        if (h[static_cast<size_t>(b) * 8 + j]) { a[j] += static_cast<double>(h[static_cast<size_t>(b) * 8 + j]); ++cnt[j]; }
+    for (int j = 0; j < 8; ++j) if (cnt[j]) a[j] /= cnt[j];
+    fprintf(stderr, "[dbg_times] grid %ux%d MT=%d n_tile=%d trips=%d | mma: total %.0f wait_acc %.0f wait_a %.0f wait_b %.0f | "
                     "epi: total %.0f wait_acc_full %.0f | prodA: total %.0f wait_a_empty %.0f (cycles, mean over CTAs)\n",
-            L.grid.x, L.grid.y, L.p.MT, L.p.n_tile, L.p.trips, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+            L.grid.x, L.p.two ? 2 : 1, L.p.MT, L.p.n_tile, (L.p.n_items + nb / (L.p.two ? 2 : 1) - 1) / (nb / (L.p.two ? 2 : 1)),
+            a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
   }
   return DLQ_OK;
 }
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {
-  switch (L.rowb) {
-    case 32: return launch_t<32>(ctx, L);
-    case 64: return launch_t<64>(ctx, L);
-    case 128: return launch_t<128>(ctx, L);
+  if (L.p.two) {
+    switch (L.rowb) {
+      case 32: return launch_t<32, true>(ctx, L);
+      case 64: return launch_t<64, true>(ctx, L);
+      case 128: return launch_t<128, true>(ctx, L);
+    }
+  } else {
+    switch (L.rowb) {
+      case 32: return launch_t<32, false>(ctx, L);
+      case 64: return launch_t<64, false>(ctx, L);
+      case 128: return launch_t<128, false>(ctx, L);
+    }
   }
   ctx->err = "internal: bad rowb";
   return DLQ_ERR_ARG;

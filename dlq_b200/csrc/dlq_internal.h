@@ -80,7 +80,8 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
 // PR the conv requires of its input tensor (and whether the image pitch must be even)
 int conv_required_in_pr(const dlq_conv_weights* w);
 struct ConvLaunch {
-  CUtensorMap tmap;
+  CUtensorMap tmap;     // activations (row-padded NHWC), 3-D
+  CUtensorMap tmap_w;   // packed weight image, 2-D
   ConvKernelParams p;
   dim3 grid, block;
   size_t smem = 0;

@@ -199,11 +199,62 @@ __global__ void __launch_bounds__(160, 1) tmem_ld_rate(int iters, int with_mma, 
   if (threadIdx.x < 32) tmem_dealloc(tmem, 512);
 }
 
+// CTA-pair test: cluster of two CTAs, the rank-0 CTA issues tcgen05.mma.cta_group::2 (M = 256, N = n) in a tight loop.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_pair_rate(int n, int iters, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (threadIdx.x < 32) { tmem_alloc_pair(&slot, 512); tmem_relinquish_pair(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  const int rank = cluster_ctarank();
+  if (threadIdx.x < 32 && rank == 0) {
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_s8(256, n);
+    const uint64_t ad0 = umma_smem_desc(smem_u32(smem), 0, 1024, UMMA_SWZ_128B);
+    const uint64_t bd0 = umma_smem_desc(smem_u32(smem + 64 * 1024), 0, 1024, UMMA_SWZ_128B);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; i += 4) {
+      if (leader) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_i8_pair(tmem + ((j & 1) ? 256u : 0u), ad0 + 2u * j, bd0 + 2u * j, idesc, 1u);
+      }
+      __syncwarp();
+    }
+    if (leader) umma_commit_pair(&bar);
+    mbar_wait(&bar, 0);
+    long long t2 = clock64();
+    if (blockIdx.x == 0 && leader) out[0] = t2 - t0;
+  } else if (threadIdx.x < 32) {
+    mbar_wait(&bar, 0);     // the multicast commit also lands here
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) tmem_dealloc_pair(tmem, 512);
+}
+
 int main() {
   long long* d;
   cudaMalloc(&d, 64);
   cudaFuncSetAttribute(mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   const int iters = 8192;
+  cudaFuncSetAttribute(mma_pair_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  for (int n : {64, 128, 256}) {
+    cudaMemset(d, 0, 32);
+    mma_pair_rate<<<148, 128, 200 * 1024>>>(n, 4096, d);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("pair error %s\n", cudaGetErrorString(e)); return 1; }
+    long long h;
+    cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+    printf("pair (cta_group::2, M=256) N=%3d: %.1f cyc/MMA\n", n, (double)h / 4096);
+  }
   cudaFuncSetAttribute(tmem_ld_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   for (int with_mma : {0, 1}) {
     cudaMemset(d, 0, 32);
