@@ -235,9 +235,10 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
 // ----------------------------------------------------------------------------------------------
 constexpr uint32_t kLeaderCtaMask = 0xFEFFFFFFu;
 __device__ __forceinline__ uint32_t leader_cta_addr(const void* smem_ptr) { return smem_u32(smem_ptr) & kLeaderCtaMask; }
-// arrive (release at cluster scope) on a barrier given by its shared::cluster address
+// arrive on a barrier given by its shared::cluster address (possibly in the peer CTA).  Default semantics
+// (release at CTA scope): a cluster-scope release would first wait for the thread's outstanding global stores.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
