@@ -255,6 +255,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const int n_tiles = w->OC / w->n_tile;
   p.n_tiles = n_tiles;
   p.two = (w->n_tile == 128 && p.Wp <= kTileM && !getenv("DLQ_DBG_NO_PAIR")) ? 1 : 0;
+  if (getenv("DLQ_DBG_PAIR64") && w->n_tile == 64 && p.Wp <= 2 * kTileM && (w->kind != CONV_STEM || atoi(getenv("DLQ_DBG_PAIR64")) > 1)) p.two = 1;
   const int ncta = p.two ? 2 : 1;
   p.w_rows = w->n_tile / ncta;
   p.step_bytes = static_cast<uint32_t>(p.w_rows) * rowb;

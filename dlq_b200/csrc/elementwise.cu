@@ -222,54 +222,77 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
 // max-pool 3x3 / s2 / p1 on row-padded NHWC int8; one thread = 16 channels of one output pixel.
 // (geometry of K/maxpool2d.cu:14-40; OOB taps skipped, int8 max is exact after quantisation)
 // ------------------------------------------------------------------------------------------------
+// Signed bytes are widened to two s16x2 words (even / odd bytes, PRMT sign-replicate) so the window maximum runs on the
+// native 16-bit SIMD 3-input max (DPX, __vimax3_s16x2) instead of the multi-instruction software __vmaxs4.
+struct S16Pair { uint32_t e, o; };   // even bytes, odd bytes, each sign-extended to 16 bits
+__device__ __forceinline__ S16Pair widen_s8x4(uint32_t v) {
+  S16Pair r;
+  asm("prmt.b32 %0, %1, %1, 0xA280;" : "=r"(r.e) : "r"(v));   // (b0, sign b0, b2, sign b2)
+  asm("prmt.b32 %0, %1, %1, 0xB391;" : "=r"(r.o) : "r"(v));   // (b1, sign b1, b3, sign b3)
+  return r;
+}
+__device__ __forceinline__ S16Pair max3(const S16Pair& a, const S16Pair& b, const S16Pair& c) {
+  S16Pair r;
+  r.e = __vimax3_s16x2(a.e, b.e, c.e);
+  r.o = __vimax3_s16x2(a.o, b.o, c.o);
+  return r;
+}
+__device__ __forceinline__ uint32_t narrow_s8x4(const S16Pair& a) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, 0x6240;" : "=r"(r) : "r"(a.e), "r"(a.o));   // (e.b0, o.b0, e.b2, o.b2)
+  return r;
+}
+
 __global__ void maxpool_act_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int N, int H, int W,
                                    int C, int PRi, int OH, int OW, int PRo) {
   // one thread = 16 channels of a 2x2 block of output pixels: 5x5 input pixels (25 x 16-byte loads for 4
   // outputs instead of 36), rows streamed through a horizontal 3-max then combined vertically.
+  // Taps outside the image are skipped in the reference (K/maxpool2d.cu:31,35) == they contribute -128 here.
   const int cv = C / 16;
   const int OH2 = (OH + 1) / 2, OW2 = (OW + 1) / 2;
   const size_t total = static_cast<size_t>(N) * OH2 * OW2 * cv;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const S16Pair kMin = {0xFF80FF80u, 0xFF80FF80u};   // -128 in every 16-bit lane
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int c16 = static_cast<int>(i % cv);
     const int ow0 = 2 * static_cast<int>((i / cv) % OW2);
     const int oh0 = 2 * static_cast<int>((i / (static_cast<size_t>(cv) * OW2)) % OH2);
     const int n = static_cast<int>(i / (static_cast<size_t>(cv) * OW2 * OH2));
-    uint32_t m[2][2][4];
+    const int ih0 = oh0 * 2 - 1, iw0 = ow0 * 2 - 1;
+    S16Pair m[2][2][4];      // running maxima of the 2x2 outputs
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[a][b][j] = 0x80808080u;
-    const int ih0 = oh0 * 2 - 1, iw0 = ow0 * 2 - 1;
+        for (int j = 0; j < 4; ++j) m[a][b][j] = kMin;
 #pragma unroll
     for (int rr = 0; rr < 5; ++rr) {
       const int ih = ih0 + rr;
-      if (ih < 0 || ih >= H) continue;
-      const size_t row = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + ih;
-      uint32_t h[2][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) h[0][j] = h[1][j] = 0x80808080u;
+      const bool row_ok = ih >= 0 && ih < H;
+      const size_t row = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + (row_ok ? ih : 0);
+      S16Pair px[5][4];
 #pragma unroll
       for (int cc = 0; cc < 5; ++cc) {
         const int iw = iw0 + cc;
-        if (iw < 0 || iw >= W) continue;
-        const int4 v = __ldg(reinterpret_cast<const int4*>(in + (row * W + iw) * C) + c16);
-        const uint32_t u[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        if (row_ok && iw >= 0 && iw < W) {
+          const int4 v = __ldg(reinterpret_cast<const int4*>(in + (row * W + iw) * C) + c16);
+          px[cc][0] = widen_s8x4(static_cast<uint32_t>(v.x));
+          px[cc][1] = widen_s8x4(static_cast<uint32_t>(v.y));
+          px[cc][2] = widen_s8x4(static_cast<uint32_t>(v.z));
+          px[cc][3] = widen_s8x4(static_cast<uint32_t>(v.w));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (cc <= 2) h[0][j] = __vmaxs4(h[0][j], u[j]);
-          if (cc >= 2) h[1][j] = __vmaxs4(h[1][j], u[j]);
+          for (int j = 0; j < 4; ++j) px[cc][j] = kMin;
         }
       }
 #pragma unroll
-      for (int b = 0; b < 2; ++b)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (rr <= 2) m[0][b][j] = __vmaxs4(m[0][b][j], h[b][j]);
-          if (rr >= 2) m[1][b][j] = __vmaxs4(m[1][b][j], h[b][j]);
-        }
+      for (int j = 0; j < 4; ++j) {
+        const S16Pair h0 = max3(px[0][j], px[1][j], px[2][j]);   // horizontal 3-max for the two output columns
+        const S16Pair h1 = max3(px[2][j], px[3][j], px[4][j]);
+        if (rr <= 2) { m[0][0][j] = max3(m[0][0][j], h0, h0); m[0][1][j] = max3(m[0][1][j], h1, h1); }
+        if (rr >= 2) { m[1][0][j] = max3(m[1][0][j], h0, h0); m[1][1][j] = max3(m[1][1][j], h1, h1); }
+      }
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -278,10 +301,105 @@ __global__ void maxpool_act_kernel(const int8_t* __restrict__ in, int8_t* __rest
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         if (ow0 + b >= OW) continue;
-        reinterpret_cast<int4*>(out + (orow * OW + ow0 + b) * C)[c16] =
-            make_int4((int)m[a][b][0], (int)m[a][b][1], (int)m[a][b][2], (int)m[a][b][3]);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = narrow_s8x4(m[a][b][j]);
+        reinterpret_cast<int4*>(out + (orow * OW + ow0 + b) * C)[c16] = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
       }
     }
+  }
+}
+
+
+// Staged variant (the network's path): a persistent CTA streams whole input-row slabs (the 2*TR+1 rows feeding TR
+// output rows of one image are contiguous in the row-padded NHWC tensor) into shared memory with ONE bulk async copy
+// per tile, double buffered.  A thread owns one (output column, 16-channel group) strip of the tile and walks the
+// slab rows once: per row three 16-byte shared loads -> widen -> horizontal 3-max, shared by the (up to two) output
+// rows the input row feeds.  Taps outside the image are replaced by a duplicate of an inside tap (max is idempotent),
+// which is what skipping them (K/maxpool2d.cu:31,35) computes.
+template <int TR>
+__global__ void __launch_bounds__(256, 1)
+maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int N, int H, int W, int C, int PRi, int OH,
+                    int OW, int PRo) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];
+  __shared__ __align__(8) uint64_t full[2];
+  constexpr int kSlabRows = 2 * TR + 1;
+  const size_t row_bytes = static_cast<size_t>(W) * C;
+  const size_t slab_bytes = kSlabRows * row_bytes;
+  const int tiles_per_img = (OH + TR - 1) / TR;
+  const int n_tiles = N * tiles_per_img;
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  // slab of tile t: input rows [2*oh0 - 1, 2*oh0 + 2*TR - 1] clipped to the image; slot r of the buffer holds row 2*oh0-1+r
+  auto issue = [&](int t, int stage) {
+    const int n = t / tiles_per_img, oh0 = (t - n * tiles_per_img) * TR;
+    const int ih_lo = max(2 * oh0 - 1, 0), ih_hi = min(2 * oh0 + 2 * TR - 1, H - 1);
+    const size_t prow = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + ih_lo;
+    const uint32_t bytes = static_cast<uint32_t>((ih_hi - ih_lo + 1) * row_bytes);
+    uint8_t* dst = pool_smem + stage * slab_bytes + static_cast<size_t>(ih_lo - (2 * oh0 - 1)) * row_bytes;
+    mbar_expect_tx(&full[stage], bytes);
+    bulk_g2s(dst, in + prow * row_bytes, bytes, &full[stage]);
+  };
+  const int cv = C / 16;
+  uint32_t ph[2] = {0, 0};
+  int k = 0;
+  if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < n_tiles) issue(blockIdx.x, 0);
+  const S16Pair kMin = {0xFF80FF80u, 0xFF80FF80u};
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+    const int stage = k & 1;
+    const int tn = t + gridDim.x;
+    if (threadIdx.x == 0 && tn < n_tiles) issue(tn, stage ^ 1);   // the other buffer was released by the barrier below
+    mbar_wait(&full[stage], ph[stage]);
+    ph[stage] ^= 1u;
+    const int n = t / tiles_per_img, oh0 = (t - n * tiles_per_img) * TR;
+    const uint8_t* slab = pool_smem + stage * slab_bytes;
+    const int ih_base = 2 * oh0 - 1;
+    for (int i = threadIdx.x; i < OW * cv; i += blockDim.x) {
+      const int c16 = i % cv;
+      const int ow = i / cv;
+      // the three taps' pixel offsets, out-of-image ones replaced by an in-image duplicate
+      const int iw1 = min(2 * ow, W - 1);
+      const int iw0 = max(2 * ow - 1, 0), iw2 = min(2 * ow + 1, W - 1);
+      const uint32_t o0 = static_cast<uint32_t>(iw0) * C + c16 * 16, o1 = static_cast<uint32_t>(iw1) * C + c16 * 16,
+                     o2 = static_cast<uint32_t>(iw2) * C + c16 * 16;
+      S16Pair m[TR][4];
+#pragma unroll
+      for (int r = 0; r < TR; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[r][j] = kMin;
+#pragma unroll
+      for (int rr = 0; rr < kSlabRows; ++rr) {
+        const int ih = min(max(ih_base + rr, 0), H - 1);          // clamped row (duplicate at the image edges)
+        const uint8_t* rowp = slab + static_cast<size_t>(ih - ih_base) * row_bytes;
+        const int4 v0 = *reinterpret_cast<const int4*>(rowp + o0);
+        const int4 v1 = *reinterpret_cast<const int4*>(rowp + o1);
+        const int4 v2 = *reinterpret_cast<const int4*>(rowp + o2);
+        const uint32_t w0[4] = {(uint32_t)v0.x, (uint32_t)v0.y, (uint32_t)v0.z, (uint32_t)v0.w};
+        const uint32_t w1[4] = {(uint32_t)v1.x, (uint32_t)v1.y, (uint32_t)v1.z, (uint32_t)v1.w};
+        const uint32_t w2[4] = {(uint32_t)v2.x, (uint32_t)v2.y, (uint32_t)v2.z, (uint32_t)v2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const S16Pair h = max3(widen_s8x4(w0[j]), widen_s8x4(w1[j]), widen_s8x4(w2[j]));
+          // slab row rr is the first row of output rr/2 (rr even), its middle row (rr odd), and the last row of rr/2 - 1
+          if (rr / 2 < TR) m[rr / 2][j] = max3(m[rr / 2][j], h, h);
+          if ((rr & 1) == 0 && rr >= 2) m[rr / 2 - 1][j] = max3(m[rr / 2 - 1][j], h, h);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        const int oh = oh0 + r;
+        if (oh < OH) {
+          const size_t orow = static_cast<size_t>(PRo) + static_cast<size_t>(n) * (OH + PRo) + oh;
+          reinterpret_cast<int4*>(out + (orow * OW + ow) * C)[c16] = make_int4(
+              (int)narrow_s8x4(m[r][0]), (int)narrow_s8x4(m[r][1]), (int)narrow_s8x4(m[r][2]), (int)narrow_s8x4(m[r][3]));
+        }
+      }
+    }
+    __syncthreads();      // everyone is done reading this buffer before it is refilled (two iterations ahead)
   }
 }
 
@@ -566,6 +684,26 @@ int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float 
 }
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
   DLQ_ARG(ctx, in.C % 16 == 0 && out.C == in.C && out.N == in.N, "maxpool geometry");
+  // staged path: 4 output rows per tile, two slabs of 9 input rows in shared memory
+  {
+    constexpr int TR = 4;
+    const size_t row_bytes = static_cast<size_t>(in.W) * in.C;
+    const size_t smem = 2 * (2 * TR + 1) * row_bytes;
+    if (smem <= ctx->smem_optin - 4096 && row_bytes % 16 == 0 && in.H >= 2 && !getenv("DLQ_DBG_POOL_DIRECT")) {
+      static bool configured[16] = {false};
+      if (!configured[ctx->device & 15]) {
+        DLQ_CUDA(ctx, cudaFuncSetAttribute(maxpool_rows_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(ctx->smem_optin - 4096)));
+        configured[ctx->device & 15] = true;
+      }
+      const int n_tiles = in.N * ((out.H + TR - 1) / TR);
+      const int grid = std::max(1, std::min(n_tiles, ctx->num_sms));
+      maxpool_rows_kernel<TR><<<grid, 256, smem, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR, out.H,
+                                                                out.W, out.PR);
+      DLQ_CUDA(ctx, cudaGetLastError());
+      return DLQ_OK;
+    }
+  }
   const size_t total = static_cast<size_t>(in.N) * ((out.H + 1) / 2) * ((out.W + 1) / 2) * (in.C / 16);
   maxpool_act_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR,
                                                                          out.H, out.W, out.PR);
