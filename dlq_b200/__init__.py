@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
     "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
     "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
-    "dlq_resnet18_checkpoint", "dlq_resnet18_launches", "dlq_resnet18_profile", "dlq_synth_fill_f32",
+    "dlq_resnet18_checkpoint", "dlq_resnet18_graph_capture", "dlq_resnet18_graph_launch", "dlq_resnet18_launches", "dlq_resnet18_profile", "dlq_synth_fill_f32",
     "dlq_multi_create", "dlq_multi_destroy", "dlq_multi_forward_host", "dlq_multi_last_error_string",
 ]
 
@@ -119,6 +119,8 @@ def load_library() -> C.CDLL:
         "dlq_resnet18_forward": (i, [vp, vp, i, vp]),
         "dlq_resnet18_forward_host": (i, [vp, vp, i, vp]),
         "dlq_resnet18_checkpoint": (i, [vp, C.c_char_p, vp]),
+        "dlq_resnet18_graph_capture": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_graph_launch": (i, [vp]),
         "dlq_resnet18_launches": (i, [vp]),
         "dlq_resnet18_profile": (i, [vp, vp, i, vp, vp]),
         "dlq_synth_fill_f32": (None, [vp, sz, C.c_uint64, C.c_char_p, i, i, i]),
@@ -379,6 +381,13 @@ class ResNet18:
 
     def checkpoint(self, name: str, out):
         self.ctx._ck(self.ctx.lib.dlq_resnet18_checkpoint(self.h, name.encode(), _ptr(out)))
+
+    def graph_capture(self, x, logits):
+        """capture forward(x, logits) into a CUDA graph (x / logits must stay allocated); replay with graph_launch()"""
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_graph_capture(self.h, _ptr(x), x.shape[0], _ptr(logits)))
+
+    def graph_launch(self):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_graph_launch(self.h))
 
     @property
     def launches(self) -> int:

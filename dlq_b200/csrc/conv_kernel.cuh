@@ -455,6 +455,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   while (tmem_cols < acc_cols * p.acc_stages) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
+    pdl_launch_dependents();   // the next kernel on the stream may begin its prologue / weight loads as SMs free up
     // "full" barriers: one arrive (+ the transaction bytes of every CTA of the pair); "empty" / acc_full ones one
     // commit per issuer; acc_empty one arrive per epilogue warp of every CTA of the pair
     for (int i = 0; i < p.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
@@ -489,6 +490,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       uint32_t as = 0, aph = 0;
       long long t_wait = 0;
       const long long t_begin = clock64();
+      pdl_wait();   // activations come from the previous kernel(s); everything above (and the weight loads) does not
       for (int it = gid; it < p.n_items; it += G) {
         const int sp = it / p.n_tiles;
         const int st = TWO ? 2 * sp + rank : sp;
@@ -625,6 +627,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     uint32_t cs = 0, cph = 0;
     long long t_wait = 0;
     const long long t_begin = clock64();
+    pdl_wait();     // the residual is an earlier kernel's output, and our stores must not race its readers
     if (has_res && gid < p.n_items && n_pairs > 0) prefetch_pair(gid, 0);
     for (int it = gid; it < p.n_items; it += G) {
       const int sp = it / p.n_tiles;

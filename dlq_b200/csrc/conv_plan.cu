@@ -389,13 +389,17 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   cfg.blockDim = L.block;
   cfg.dynamicSmemBytes = L.smem;
   cfg.stream = ctx->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = TWO ? 2u : 1u;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: this kernel's prologue and weight loads overlap the tail of the previous kernel
+  // on the stream; the kernel itself waits (griddepcontrol.wait) before it touches activations
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("DLQ_DBG_NO_PDL") ? 1 : 2;
   DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB, TWO>, L.tmap, L.tmap_w, L.p));
   if (L.p.dbg_times) {
     cudaStreamSynchronize(ctx->stream);

@@ -351,6 +351,8 @@ struct dlq_resnet18 {
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
+  cudaGraph_t graph = nullptr;          // dlq_resnet18_graph_capture / _launch
+  cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t copy_stream = nullptr;   // forward_host pipelining
   cudaEvent_t copy_done[64] = {nullptr};
   cudaEvent_t compute_done = nullptr;
@@ -435,6 +437,8 @@ void dlq_resnet18_destroy(dlq_resnet18* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->graph) cudaGraphDestroy(m->graph);
   for (void* p : m->allocs) cudaFree(p);
   for (auto& c : m->conv) dlq_conv_weights_free(c);
   if (m->copy_stream) {
@@ -627,6 +631,32 @@ int dlq_resnet18_profile(dlq_resnet18* m, const float* x, int N, float* logits, 
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return rc;
+}
+
+int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* logits) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  // a plain forward first: builds the launch plans and sets the kernels' shared-memory attributes outside the capture
+  int rc = forward_impl(m, x, N, logits, nullptr);
+  if (rc != DLQ_OK) return rc;
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+  if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
+  DLQ_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  rc = forward_impl(m, x, N, logits, nullptr);
+  const cudaError_t e = cudaStreamEndCapture(ctx->stream, &m->graph);
+  if (rc != DLQ_OK) return rc;
+  DLQ_CUDA(ctx, e);
+  DLQ_CUDA(ctx, cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+  return DLQ_OK;
+}
+
+int dlq_resnet18_graph_launch(dlq_resnet18* m) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, m->graph_exec != nullptr, "no graph captured (call dlq_resnet18_graph_capture first)");
+  DLQ_CUDA(ctx, cudaGraphLaunch(m->graph_exec, ctx->stream));
+  return DLQ_OK;
 }
 
 int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {

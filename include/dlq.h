@@ -172,6 +172,12 @@ int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float
  * (names as R/infer_e2e.cu:297-426 dumps them).  out is a device pointer. */
 int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);
 /* number of kernel launches one forward enqueues (for accounting) */
+/* Latency path (BASELINE config "batch 1"): capture one forward of batch N (x -> logits, both device pointers that
+ * stay valid) into a CUDA graph once, then replay it with a single launch.  The reference instead pays ~45 launches,
+ * allocations and weight uploads per image (R/infer_e2e.cu:230-441).  dlq_resnet18_graph_launch enqueues on the
+ * context's stream and does not synchronise. */
+int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* logits);
+int dlq_resnet18_graph_launch(dlq_resnet18* m);
 int dlq_resnet18_launches(const dlq_resnet18* m);
 /* one forward with a CUDA event between launches; ms[dlq_resnet18_launches()] receives each launch's device
  * time in order: quantise+s2d, stem conv, max-pool, per block conv1,[downsample],conv2, GAP+FC.  Synchronises.
