@@ -32,6 +32,8 @@ ACT_INPUT, ACT_STEM, ACT_GAP = 0, 1, 26
 ABI_SYMBOLS = [
     "dlq_create", "dlq_destroy", "dlq_last_error_string", "dlq_sync", "dlq_stream", "dlq_set_stream", "dlq_version",
     "dlq_quantize_f32_i8", "dlq_dequantize_i8_f32", "dlq_dequantize_i8_f32_per_channel",
+    "dlq_quantize_f32_e4m3", "dlq_dequantize_e4m3_f32", "dlq_conv_weights_pack_fp8", "dlq_conv_weights_pack_e4m3",
+    "dlq_f32_to_e4m3", "dlq_conv2d_fp8",
     "dlq_conv_weights_pack", "dlq_conv_weights_pack_i8", "dlq_conv_weights_free", "dlq_conv2d_i8", "dlq_fold_bn",
     "dlq_res_mul", "dlq_act_bytes", "dlq_conv_required_pad_rows", "dlq_conv2d_i8_act", "dlq_act_from_nchw_i8",
     "dlq_act_to_nchw_i8", "dlq_stem_pack_input_i8", "dlq_conv_plan_create", "dlq_conv_plan_launch",
@@ -63,7 +65,7 @@ class _ResNet18Weights(C.Structure):
     _fields_ = [("conv_w", C.c_void_p * NUM_CONVS), ("bn_gamma", C.c_void_p * NUM_CONVS),
                 ("bn_beta", C.c_void_p * NUM_CONVS), ("bn_mean", C.c_void_p * NUM_CONVS),
                 ("bn_var", C.c_void_p * NUM_CONVS), ("fc_w", C.c_void_p), ("fc_b", C.c_void_p),
-                ("act_scale", C.c_float * NUM_ACTS)]
+                ("act_scale", C.c_float * NUM_ACTS), ("fp8", C.c_int)]
 
 
 _lib = None
@@ -89,6 +91,12 @@ def load_library() -> C.CDLL:
         "dlq_quantize_f32_i8": (i, [vp, vp, sz, f, vp]),
         "dlq_dequantize_i8_f32": (i, [vp, vp, sz, f, vp]),
         "dlq_dequantize_i8_f32_per_channel": (i, [vp, vp, i, i, i, vp, vp]),
+        "dlq_quantize_f32_e4m3": (i, [vp, vp, sz, f, vp]),
+        "dlq_dequantize_e4m3_f32": (i, [vp, vp, sz, f, vp]),
+        "dlq_conv_weights_pack_fp8": (i, [vp, vp, i, i, i, i, i, i, i, i, vp, C.POINTER(vp)]),
+        "dlq_conv_weights_pack_e4m3": (i, [vp, vp, i, i, i, i, i, i, i, i, C.POINTER(vp)]),
+        "dlq_f32_to_e4m3": (C.c_uint8, [f]),
+        "dlq_conv2d_fp8": (i, [vp, vp, i, i, i, i, vp, C.POINTER(_Epilogue), vp, vp, C.POINTER(i), C.POINTER(i)]),
         "dlq_conv_weights_pack": (i, [vp, vp, i, i, i, i, i, i, i, i, vp, C.POINTER(vp)]),
         "dlq_conv_weights_pack_i8": (i, [vp, vp, i, i, i, i, i, i, i, i, C.POINTER(vp)]),
         "dlq_conv_weights_free": (None, [vp]),
@@ -241,6 +249,41 @@ class Context:
                                                    C.byref(h)))
         return ConvWeights(self, h, None, oc)
 
+    # ---- FP8 (E4M3) variants, QUANT_SPEC section 6
+    def quantize_f32_e4m3(self, x, scale: float, q):
+        self._ck(self.lib.dlq_quantize_f32_e4m3(self.h, _ptr(x), x.numel(), scale, _ptr(q)))
+
+    def dequantize_e4m3_f32(self, q, scale: float, x):
+        self._ck(self.lib.dlq_dequantize_e4m3_f32(self.h, _ptr(q), q.numel(), scale, _ptr(x)))
+
+    def pack_conv_weights_fp8(self, w_oihw: np.ndarray, stride: int, pad: int) -> ConvWeights:
+        w = np.ascontiguousarray(w_oihw, dtype=np.float32)
+        oc, ic, kh, kw = w.shape
+        scale = np.empty(oc, dtype=np.float32)
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_conv_weights_pack_fp8(self.h, w.ctypes.data, oc, ic, kh, kw, stride, stride, pad, pad,
+                                                    scale.ctypes.data, C.byref(h)))
+        return ConvWeights(self, h, scale, oc)
+
+    def pack_conv_weights_e4m3(self, wq_oihw: np.ndarray, stride: int, pad: int) -> ConvWeights:
+        w = np.ascontiguousarray(wq_oihw, dtype=np.uint8)
+        oc, ic, kh, kw = w.shape
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_conv_weights_pack_e4m3(self.h, w.ctypes.data, oc, ic, kh, kw, stride, stride, pad, pad,
+                                                     C.byref(h)))
+        return ConvWeights(self, h, None, oc)
+
+    def conv2d_fp8(self, x, w: ConvWeights, alpha=None, beta=None, residual=None, res_mul: float = 0.0,
+                   relu: bool = False, y=None, acc_out=None):
+        """x / y / residual: uint8 E4M3 codes NCHW; acc_out: float32 NCHW raw accumulators"""
+        n, c, hh, ww = x.shape
+        ep = _Epilogue(_ptr(alpha), _ptr(beta), _ptr(residual), res_mul, int(relu))
+        oh, ow = C.c_int(), C.c_int()
+        self._ck(self.lib.dlq_conv2d_fp8(self.h, _ptr(x), n, c, hh, ww, w.handle,
+                                         C.byref(ep) if alpha is not None else None, _ptr(y), _ptr(acc_out),
+                                         C.byref(oh), C.byref(ow)))
+        return oh.value, ow.value
+
     def conv2d_i8(self, x, w: ConvWeights, alpha=None, beta=None, residual=None, res_mul: float = 0.0,
                   relu: bool = False, y=None, acc_out=None):
         """alpha/beta/res_mul are requantisation multipliers (output scale folded in, see fold_bn)."""
@@ -330,7 +373,7 @@ class Context:
         self._ck(self.lib.dlq_softmax_f32(self.h, _ptr(x), n, k, _ptr(y)))
 
 
-def _weights_struct(weights: Dict[str, np.ndarray], act_scale) -> tuple:
+def _weights_struct(weights: Dict[str, np.ndarray], act_scale, fp8: bool = False) -> tuple:
     """Build the dlq_resnet18_weights struct from a dict keyed like the reference's <key>.bin export
     (tools/export_resnet18.py:85-92); returns (struct, keepalive list)."""
     from .synth import conv_keys
@@ -356,15 +399,17 @@ def _weights_struct(weights: Dict[str, np.ndarray], act_scale) -> tuple:
     s.fc_w, s.fc_b = fw.ctypes.data, fb.ctypes.data
     for i in range(NUM_ACTS):
         s.act_scale[i] = float(act_scale[i])
+    s.fp8 = 1 if fp8 else 0
     return s, keep
 
 
 class ResNet18:
     """Whole-network INT8 runner (replaces main() of runtime/infer_e2e.cu for a batch)."""
 
-    def __init__(self, ctx: Context, weights: Dict[str, np.ndarray], act_scale, max_batch: int):
+    def __init__(self, ctx: Context, weights: Dict[str, np.ndarray], act_scale, max_batch: int, fp8: bool = False):
+        """fp8=True: E4M3 weights / activations with FP32 accumulation (act_scale maps absmax to 448)"""
         self.ctx = ctx
-        s, keep = _weights_struct(weights, act_scale)
+        s, keep = _weights_struct(weights, act_scale, fp8)
         h = C.c_void_p()
         ctx._ck(ctx.lib.dlq_resnet18_create(ctx.h, C.byref(s), max_batch, C.byref(h)))
         self.h = h

@@ -35,6 +35,7 @@
 //   stages (acc_full/acc_empty).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp8.h>
 #include "sm100_ptx.cuh"
 
 namespace dlq {
@@ -122,9 +123,11 @@ struct IssuerCtx {
   int dbg;
 };
 
-template <bool TWO>
+// FP8: E4M3 x E4M3 -> FP32 (kind::f8f6f4) instead of S8 x S8 -> S32 (kind::i8); same operand bytes, same descriptors
+template <bool TWO, bool FP8>
 __device__ __forceinline__ void umma_issue(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  if (TWO) umma_i8_pair(d, a, b, idesc, acc); else umma_i8(d, a, b, idesc, acc);
+  if (FP8) { if (TWO) umma_f8_pair(d, a, b, idesc, acc); else umma_f8(d, a, b, idesc, acc); }
+  else { if (TWO) umma_i8_pair(d, a, b, idesc, acc); else umma_i8(d, a, b, idesc, acc); }
 }
 template <bool TWO>
 __device__ __forceinline__ void umma_done(uint64_t* bar) {
@@ -132,7 +135,7 @@ __device__ __forceinline__ void umma_done(uint64_t* bar) {
 }
 
 // KSEL: 0 = every K=32 slice of the step, 1 / 2 = first / second half of them (two issuers sharing ONE accumulator)
-template <int ROWB, int MYMT, bool FIRST, bool TWO, int KSEL>
+template <int ROWB, int MYMT, bool FIRST, bool TWO, int KSEL, bool FP8>
 __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_t a_lo, uint32_t b_lo, uint32_t d0,
                                            uint32_t n_tile, uint32_t idesc) {
   constexpr int K32 = ROWB / 32;
@@ -143,17 +146,17 @@ __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_
   for (int kk = KK0; kk < KK1; ++kk) {
 #pragma unroll
     for (int mt = 0; mt < MYMT; ++mt) {   // tile inner: consecutive MMAs hit different accumulators
-      umma_issue<TWO>(d0 + (mt ? n_tile : 0u), (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),
+      umma_issue<TWO, FP8>(d0 + (mt ? n_tile : 0u), (static_cast<uint64_t>(a_hi) << 32) | (a_lo + mt * TILE16 + 2u * kk),
                       (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc, (FIRST && kk == KK0) ? 0u : 1u);
     }
   }
 }
 
-template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL>
+template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL, bool FP8>
 __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out) {
   constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
   constexpr uint32_t SBO = 8u * ROWB;
-  const uint32_t idesc = umma_idesc_s8(TWO ? 2 * kTileM : kTileM, c.n_tile);
+  const uint32_t idesc = FP8 ? umma_idesc_e4m3(TWO ? 2 * kTileM : kTileM, c.n_tile) : umma_idesc_s8(TWO ? 2 * kTileM : kTileM, c.n_tile);
   const uint32_t a_hi = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT) >> 32);
   const uint32_t b_hi = a_hi;
   const uint32_t a_flags = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT)) + (c.sA_u32 >> 4) + c.tile_off16;
@@ -197,7 +200,7 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
           // K-split: the second issuer only accumulates, and only after the first one has issued the overwriting MMA
           if (KSEL == 2) mbar_wait(&c.k_first[cs], cph);
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
           if (KSEL == 1) mbar_arrive(&c.k_first[cs]);
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
@@ -213,7 +216,7 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false, TWO, KSEL>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
@@ -293,7 +296,18 @@ __device__ __forceinline__ void fma2_rn(float& d0, float& d1, float a0, float a1
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
 }
 
-template <bool HAS_RES, int NU, bool SAME_CB, bool ACC_OUT = false>
+// E4M3 helpers (QUANT_SPEC section 6): float -> e4m3 is round-to-nearest-even, saturating to +-448
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+__device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t two_bytes) {
+  const __half2_raw h = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(two_bytes), __NV_E4M3);
+  return __half22float2(*reinterpret_cast<const __half2*>(&h));
+}
+
+template <bool HAS_RES, int NU, bool SAME_CB, bool ACC_OUT, bool FP8>
 __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCtx& e, const uint32_t (&taddr)[2],
                                           const int (&c0)[2], const int (&g_own)[2], bool release_acc,
                                           uint32_t acc_empty_addr) {
@@ -356,18 +370,30 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
 #pragma unroll
       for (int u = 0; u < NU; ++u) {
         float t0, t1, t2, t3;
-        fma2_rn(t0, t1, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 0])),
-                static_cast<float>(static_cast<int32_t>(v[u][4 * j + 1])), al[u].x, al[u].y, be[u].x, be[u].y);
-        fma2_rn(t2, t3, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 2])),
-                static_cast<float>(static_cast<int32_t>(v[u][4 * j + 3])), al[u].z, al[u].w, be[u].z, be[u].w);
+        if (FP8) {
+          fma2_rn(t0, t1, __uint_as_float(v[u][4 * j + 0]), __uint_as_float(v[u][4 * j + 1]), al[u].x, al[u].y, be[u].x, be[u].y);
+          fma2_rn(t2, t3, __uint_as_float(v[u][4 * j + 2]), __uint_as_float(v[u][4 * j + 3]), al[u].z, al[u].w, be[u].z, be[u].w);
+        } else {
+          fma2_rn(t0, t1, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 0])),
+                  static_cast<float>(static_cast<int32_t>(v[u][4 * j + 1])), al[u].x, al[u].y, be[u].x, be[u].y);
+          fma2_rn(t2, t3, static_cast<float>(static_cast<int32_t>(v[u][4 * j + 2])),
+                  static_cast<float>(static_cast<int32_t>(v[u][4 * j + 3])), al[u].z, al[u].w, be[u].z, be[u].w);
+        }
         if (HAS_RES) {
           const uint32_t w = reinterpret_cast<const uint32_t*>(rv[u])[j];
-          fma2_rn(t0, t1, static_cast<float>(static_cast<int8_t>(w)), static_cast<float>(static_cast<int8_t>(w >> 8)),
-                  e.res_mul, e.res_mul, t0, t1);
-          fma2_rn(t2, t3, static_cast<float>(static_cast<int8_t>(w >> 16)), static_cast<float>(static_cast<int8_t>(w >> 24)),
-                  e.res_mul, e.res_mul, t2, t3);
+          if (FP8) {
+            const float2 r01 = e4m3x2_to_float2(w & 0xFFFFu), r23 = e4m3x2_to_float2(w >> 16);
+            fma2_rn(t0, t1, r01.x, r01.y, e.res_mul, e.res_mul, t0, t1);
+            fma2_rn(t2, t3, r23.x, r23.y, e.res_mul, e.res_mul, t2, t3);
+          } else {
+            fma2_rn(t0, t1, static_cast<float>(static_cast<int8_t>(w)), static_cast<float>(static_cast<int8_t>(w >> 8)),
+                    e.res_mul, e.res_mul, t0, t1);
+            fma2_rn(t2, t3, static_cast<float>(static_cast<int8_t>(w >> 16)), static_cast<float>(static_cast<int8_t>(w >> 24)),
+                    e.res_mul, e.res_mul, t2, t3);
+          }
         }
-        const uint32_t q = pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2), __float2int_rn(t3));
+        const uint32_t q = FP8 ? pack_e4m3x4(t0, t1, t2, t3)
+                               : pack_sat_s8x4(__float2int_rn(t0), __float2int_rn(t1), __float2int_rn(t2), __float2int_rn(t3));
         // ReLU on the packed bytes: replicate each byte's sign (PRMT mode 8+i) and clear the negative ones
         uint32_t sgn;
         asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(sgn) : "r"(q));
@@ -410,7 +436,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha, beta: 2*OC f32]
 //   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
-template <int ROWB, bool TWO>
+template <int ROWB, bool TWO, bool FP8>
 __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmw, const ConvKernelParams p) {
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
@@ -570,12 +596,12 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const long long t_begin = clock64();
     if (k_split) {
       constexpr int KA = K32 >= 2 ? 1 : 0, KB = K32 >= 2 ? 2 : 0;   // (K32 == 1 never takes this branch)
-      if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB>(c, tt); }
-      else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB>(c, tt); }
+      if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
+      else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8>(c, tt); }
     } else if (p.b_resident) {
-      if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0>(c, tt);
+      if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0, FP8>(c, tt);
     } else {
-      if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0>(c, tt);
+      if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0, FP8>(c, tt);
     }
     if (p.dbg_times && c.leader && issuer == 0) {
       long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
@@ -660,7 +686,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           cp_async_wait_all();
           __syncwarp();
         }
-#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC>(p, e, taddr, c0, g_own, last, acc_empty_addr)
+#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC, FP8>(p, e, taddr, c0, g_own, last, acc_empty_addr)
 #define DLQ_EPI_SHAPES(RES)                                       \
   do {                                                            \
     if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \

@@ -184,6 +184,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
               const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L) {
   ConvKernelParams& p = L->p;
   memset(&p, 0, sizeof(p));
+  L->fp8 = w->fp8;
   const int rowb = w->rowb;
   L->rowb = rowb;
   int es = 1;
@@ -376,11 +377,11 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   return DLQ_OK;
 }
 
-template <int ROWB, bool TWO>
+template <int ROWB, bool TWO, bool FP8>
 static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   static size_t configured[16] = {0};   // per-device max dynamic smem already requested
   if (configured[ctx->device & 15] < L.smem) {
-    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(ctx->smem_optin)));
     configured[ctx->device & 15] = ctx->smem_optin;
   }
@@ -400,7 +401,7 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = getenv("DLQ_DBG_NO_PDL") ? 1 : 2;
-  DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB, TWO>, L.tmap, L.tmap_w, L.p));
+  DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB, TWO, FP8>, L.tmap, L.tmap_w, L.p));
   if (L.p.dbg_times) {
     cudaStreamSynchronize(ctx->stream);
     const int nb = static_cast<int>(L.grid.x);
@@ -420,22 +421,20 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   return DLQ_OK;
 }
 
-int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {
-  if (L.p.two) {
-    switch (L.rowb) {
-      case 32: return launch_t<32, true>(ctx, L);
-      case 64: return launch_t<64, true>(ctx, L);
-      case 128: return launch_t<128, true>(ctx, L);
-    }
-  } else {
-    switch (L.rowb) {
-      case 32: return launch_t<32, false>(ctx, L);
-      case 64: return launch_t<64, false>(ctx, L);
-      case 128: return launch_t<128, false>(ctx, L);
-    }
+template <bool TWO, bool FP8>
+static int launch_rowb(dlq_ctx* ctx, const ConvLaunch& L) {
+  switch (L.rowb) {
+    case 32: return launch_t<32, TWO, FP8>(ctx, L);
+    case 64: return launch_t<64, TWO, FP8>(ctx, L);
+    case 128: return launch_t<128, TWO, FP8>(ctx, L);
   }
   ctx->err = "internal: bad rowb";
   return DLQ_ERR_ARG;
+}
+
+int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {
+  if (L.fp8) return L.p.two ? launch_rowb<true, true>(ctx, L) : launch_rowb<false, true>(ctx, L);
+  return L.p.two ? launch_rowb<true, false>(ctx, L) : launch_rowb<false, false>(ctx, L);
 }
 
 }  // namespace dlq

@@ -108,6 +108,39 @@ inline int8_t quant_host(float t, int lo, int hi) {
   return static_cast<int8_t>(static_cast<int>(r));
 }
 
+// float -> E4M3 (1-4-3, bias 7, max 448, no infinities), round-to-nearest-even, saturate-to-finite (QUANT_SPEC 6)
+uint8_t f32_to_e4m3_host(float f) {
+  const uint8_t sign = std::signbit(f) ? 0x80 : 0x00;
+  if (std::isnan(f)) return static_cast<uint8_t>(sign | 0x7F);
+  const float a = std::fabs(f);
+  if (a >= 448.0f) return static_cast<uint8_t>(sign | 0x7E);
+  if (a < 0.015625f) {                                  // below the smallest normal 2^-6: multiples of 2^-9
+    const int q = static_cast<int>(std::nearbyintf(a * 512.0f));    // 0..8 (8 == smallest normal, same encoding)
+    return static_cast<uint8_t>(sign | q);
+  }
+  int e;
+  const float fr = std::frexp(a, &e);                   // a = fr * 2^e, fr in [0.5, 1)
+  int ex = e - 1;                                       // a = (2 fr) * 2^ex, 2 fr in [1, 2)
+  int m = static_cast<int>(std::nearbyintf((2.0f * fr - 1.0f) * 8.0f));   // 0..8
+  if (m == 8) { m = 0; ++ex; }
+  if (ex > 8 || (ex == 8 && m == 7)) return static_cast<uint8_t>(sign | 0x7E);
+  return static_cast<uint8_t>(sign | ((ex + 7) << 3) | m);
+}
+
+void quantize_rows_e4m3(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s) {
+  q.resize(static_cast<size_t>(rows) * K);
+  s.resize(rows);
+  for (int r = 0; r < rows; ++r) {
+    float am = 0.f;
+    for (int k = 0; k < K; ++k) am = std::max(am, std::fabs(w[static_cast<size_t>(r) * K + k]));
+    const float sc = am > 0.f ? static_cast<float>(static_cast<double>(am) / 448.0) : 1.0f;
+    s[r] = sc;
+    const float inv = inv_scale(sc);
+    for (int k = 0; k < K; ++k)
+      q[static_cast<size_t>(r) * K + k] = static_cast<int8_t>(f32_to_e4m3_host(w[static_cast<size_t>(r) * K + k] * inv));
+  }
+}
+
 void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s) {
   q.resize(static_cast<size_t>(rows) * K);
   s.resize(rows);
@@ -172,6 +205,31 @@ int dlq_conv_weights_pack(dlq_ctx* ctx, const float* w_host, int OC, int IC, int
   return DLQ_OK;
 }
 
+/* E4M3 variants: the packed bytes are E4M3, the conv accumulates in FP32 on kind::f8f6f4 */
+int dlq_conv_weights_pack_e4m3(dlq_ctx* ctx, const uint8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                               int pW, dlq_conv_weights** out) {
+  const int rc = dlq_conv_weights_pack_i8(ctx, reinterpret_cast<const int8_t*>(wq), OC, IC, kH, kW, sH, sW, pH, pW, out);
+  if (rc == DLQ_OK) (*out)->fp8 = 1;
+  return rc;
+}
+
+int dlq_conv_weights_pack_fp8(dlq_ctx* ctx, const float* w_host, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
+                              int pW, float* w_scale_host, dlq_conv_weights** out) {
+  if (!ctx || !out) return DLQ_ERR_ARG;
+  *out = nullptr;
+  DLQ_ARG(ctx, w_host != nullptr && OC > 0 && IC > 0 && kH > 0 && kW > 0, "null weights or bad dims");
+  std::vector<int8_t> q;
+  std::vector<float> s;
+  quantize_rows_e4m3(w_host, OC, IC * kH * kW, q, s);
+  const int rc = dlq_conv_weights_pack_e4m3(ctx, reinterpret_cast<const uint8_t*>(q.data()), OC, IC, kH, kW, sH, sW, pH, pW, out);
+  if (rc != DLQ_OK) return rc;
+  (*out)->scale = s;
+  if (w_scale_host) std::copy(s.begin(), s.end(), w_scale_host);
+  return DLQ_OK;
+}
+
+uint8_t dlq_f32_to_e4m3(float f) { return f32_to_e4m3_host(f); }
+
 void dlq_conv_weights_free(dlq_conv_weights* w) {
   if (!w) return;
   cudaSetDevice(w->device);
@@ -179,8 +237,27 @@ void dlq_conv_weights_free(dlq_conv_weights* w) {
   delete w;
 }
 
+static int conv2d_bytes(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                       const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW);
+
 int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
                   const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, !w || !w->fp8, "weights were packed as E4M3: use dlq_conv2d_fp8");
+  return conv2d_bytes(ctx, x, N, C, H, W, w, ep, y, acc_out, OH, OW);
+}
+
+/* E4M3 activations and weights, FP32 accumulators (acc_out: raw fp32 accumulators, NCHW) */
+int dlq_conv2d_fp8(dlq_ctx* ctx, const uint8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                   const dlq_epilogue* ep, uint8_t* y, float* acc_out, int* OH, int* OW) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_ARG(ctx, w && w->fp8, "weights were not packed as E4M3");
+  return conv2d_bytes(ctx, reinterpret_cast<const int8_t*>(x), N, C, H, W, w, ep, reinterpret_cast<int8_t*>(y),
+                      reinterpret_cast<int32_t*>(acc_out), OH, OW);
+}
+
+static int conv2d_bytes(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                       const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW) {
   if (!ctx) return DLQ_ERR_ARG;
   DLQ_ARG(ctx, x && w && N >= 0 && C == w->IC && H > 0 && W > 0, "null pointer or dims do not match the packed weights");
   DLQ_ARG(ctx, (y == nullptr) || (ep != nullptr && ep->alpha && ep->beta),
@@ -335,6 +412,7 @@ struct dlq_resnet18 {
   float* d_alpha[DLQ_NUM_CONVS] = {nullptr};
   float* d_beta[DLQ_NUM_CONVS] = {nullptr};
   float act_scale[DLQ_NUM_ACTS];
+  int fp8 = 0;                // E4M3 activations / weights, FP32 accumulation (else int8 / int32)
   int8_t* d_fc_w = nullptr;
   float* d_fc_scale = nullptr;
   float* d_fc_bias = nullptr;
@@ -462,6 +540,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   m->ctx = ctx;
   m->max_batch = max_batch;
   std::copy(w->act_scale, w->act_scale + DLQ_NUM_ACTS, m->act_scale);
+  m->fp8 = w->fp8 ? 1 : 0;
 
   // ---- convs: geometry as wired by runtime/infer_e2e.cu:258-407
   struct CG { int ic, oc, k, s, p; float s_in, s_out; };
@@ -483,7 +562,8 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     DLQ_ARG(ctx, w->conv_w[i] && w->bn_gamma[i] && w->bn_beta[i] && w->bn_mean[i] && w->bn_var[i], "missing conv/bn weights");
     const CG& g = geo[i];
     std::vector<float> s_w(g.oc);
-    int rc = dlq_conv_weights_pack(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i]);
+    int rc = m->fp8 ? dlq_conv_weights_pack_fp8(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i])
+                    : dlq_conv_weights_pack(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i]);
     if (rc != DLQ_OK) return rc;
     // folded constants, QUANT_SPEC §3 (double arithmetic, rounded once)
     std::vector<float> alpha(g.oc), beta(g.oc);
@@ -499,7 +579,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   {
     std::vector<int8_t> q;
     std::vector<float> s;
-    quantize_rows(w->fc_w, 1000, 512, q, s);
+    if (m->fp8) quantize_rows_e4m3(w->fc_w, 1000, 512, q, s); else quantize_rows(w->fc_w, 1000, 512, q, s);
     std::vector<float> sc(1000), bias(w->fc_b, w->fc_b + 1000);
     for (int o = 0; o < 1000; ++o) sc[o] = static_cast<float>(static_cast<double>(w->act_scale[kActGap]) * static_cast<double>(s[o]));
     // transposed image for the fused GAP+FC kernel: [512/16][1024][16 B]
@@ -576,7 +656,7 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   };
   int rc = mark();
   if (rc != DLQ_OK) return rc;
-  rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N));
+  rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N), m->fp8);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   rc = launch_conv(ctx, P.L[0]);
@@ -600,8 +680,10 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   }
   const Act last = with_n(m->a_out[7], N);
   const float s_over_hw = static_cast<float>(static_cast<double>(S[act_out(7)]) / static_cast<double>(last.H * last.W));
-  rc = gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
-                  logits);
+  rc = m->fp8 ? gap_fc_act_e4m3(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000,
+                                m->d_gap_q, logits)
+              : gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
+                           logits);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   m->last_N = N;

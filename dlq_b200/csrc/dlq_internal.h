@@ -67,6 +67,7 @@ struct dlq_conv_weights {
   int n_steps = 0;
   uint32_t step_bytes = 0;
   uint8_t* d_img = nullptr;   // device: [OC/n_tile][n_steps][step_bytes]
+  int fp8 = 0;                // 1: the bytes are E4M3 (QUANT_SPEC section 6), else signed int8
   std::vector<int8_t> q_oihw; // host copy of the quantised weights (tests / checkpoints)
   std::vector<float> scale;   // per-output-channel scale
   int device = 0;
@@ -86,6 +87,7 @@ struct ConvLaunch {
   dim3 grid, block;
   size_t smem = 0;
   int rowb = 0;
+  int fp8 = 0;          // operands are E4M3 bytes, accumulators FP32 (else S8 / S32)
 };
 // Build the launch for conv `w` reading `in` and writing `out` (either of out.ptr / acc_out may be null).
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
@@ -98,10 +100,13 @@ int nchw_to_act_i8(dlq_ctx* ctx, const int8_t* x, const Act& a);          // den
 int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y);                // row-padded NHWC -> dense NCHW
 int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32_t* y);
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a);   // C=3 int8 NCHW -> s2d
-int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a);
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a, int fp8 = 0);
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out);
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
                const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
+
+int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
 
 void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes);
 float inv_scale(float s);

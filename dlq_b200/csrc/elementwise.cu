@@ -5,6 +5,7 @@
 // sized in multiples of the SM count with grid-stride loops.
 #include "dlq_internal.h"
 #include <algorithm>
+#include <cuda_fp8.h>
 
 namespace dlq {
 
@@ -180,7 +181,8 @@ __global__ void nhwc_to_nchw_i32_kernel(const int32_t* __restrict__ x, int32_t* 
 // One K=32 MMA then covers two horizontally adjacent taps from a normal SWIZZLE_32B K-major row.
 // One thread per s2d pixel: 6 float2 (or 6 char2) loads, two 16-byte stores (first half of pair p+2... see below).
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool QUANT>
+// QMODE: 0 = copy int8 bytes, 1 = quantise fp32 -> int8 (QUANT_SPEC 2), 2 = quantise fp32 -> E4M3 (QUANT_SPEC 6)
+template <typename T, int QMODE>
 __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
                                 float inv_s) {
   const int H2 = H / 2, W2 = W / 2, WP = W2 + 3;
@@ -196,10 +198,16 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
         const T* src = x + ((static_cast<size_t>(n) * 3 + c) * H + (2 * h2 + dy)) * W + 2 * w2;
-        if constexpr (QUANT) {
+        if constexpr (QMODE == 1) {
           const float2 v = __ldg(reinterpret_cast<const float2*>(src));
           q[dy][0][c] = quant_rn(__fmul_rn(v.x, inv_s), -128, 127);
           q[dy][1][c] = quant_rn(__fmul_rn(v.y, inv_s), -128, 127);
+        } else if constexpr (QMODE == 2) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(src));
+          const uint32_t two = __nv_cvt_float2_to_fp8x2(make_float2(__fmul_rn(v.x, inv_s), __fmul_rn(v.y, inv_s)),
+                                                       __NV_SATFINITE, __NV_E4M3);
+          q[dy][0][c] = static_cast<int>(two & 0xFFu);
+          q[dy][1][c] = static_cast<int>((two >> 8) & 0xFFu);
         } else {
           q[dy][0][c] = src[0];
           q[dy][1][c] = src[1];
@@ -215,6 +223,66 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
     int4* prow = reinterpret_cast<int4*>(a) + (row * WP) * 2;
     prow[(w2 + 2) * 2 + 0] = o;
     prow[(w2 + 1) * 2 + 1] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// E4M3 (FP8) helpers, QUANT_SPEC 6: q = e4m3_rn_satfinite(x * inv_s); x' = float(q) * s
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float e4m3_to_float(uint8_t b) {
+  const __half_raw h = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(b), __NV_E4M3);
+  return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+__device__ __forceinline__ uint8_t float_to_e4m3(float f) {
+  return static_cast<uint8_t>(__nv_cvt_float_to_fp8(f, __NV_SATFINITE, __NV_E4M3));
+}
+__global__ void quantize_f32_e4m3_kernel(const float* __restrict__ x, size_t n, float inv_s, uint8_t* __restrict__ q) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t n4 = n / 4;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(__fmul_rn(v.x, inv_s), __fmul_rn(v.y, inv_s)), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(__fmul_rn(v.z, inv_s), __fmul_rn(v.w, inv_s)), __NV_SATFINITE, __NV_E4M3);
+    reinterpret_cast<uint32_t*>(q)[i] = lo | (hi << 16);
+  }
+  for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    q[i] = float_to_e4m3(__fmul_rn(x[i], inv_s));
+}
+__global__ void dequantize_e4m3_f32_kernel(const uint8_t* __restrict__ q, size_t n, float s, float* __restrict__ x) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+    x[i] = __fmul_rn(e4m3_to_float(q[i]), s);
+}
+
+// GAP + FC for the E4M3 network (one block per image, 512 threads): channel c's mean over H*W is accumulated in
+// fp32 in pixel order, scaled, quantised to E4M3; logits[o] = fmaf(sum_c float(g[c]) * float(w[o][c]), scale[o], bias[o])
+// with the dot product accumulated in fp32 in channel order.  Weights in the int8 kernel's transposed image
+// [C/16][1024][16 B].
+__global__ void __launch_bounds__(512)
+gap_fc_e4m3_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
+                   float inv_gap_scale, const int8_t* __restrict__ fc_wT, const float* __restrict__ fc_scale,
+                   const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits) {
+  extern __shared__ float gq_s[];     // [C] dequantised (unit-scale) gap values
+  const int n = blockIdx.x;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(in) + (static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR)) * W * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int px = 0; px < H * W; ++px) s = __fadd_rn(s, e4m3_to_float(img[static_cast<size_t>(px) * C + c]));
+    const uint8_t q = float_to_e4m3(__fmul_rn(__fmul_rn(s, scale_over_hw), inv_gap_scale));
+    if (gap_q) gap_q[static_cast<size_t>(n) * C + c] = static_cast<int8_t>(q);
+    gq_s[c] = e4m3_to_float(q);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < O; o += blockDim.x) {
+    float acc = 0.f;
+    for (int kb = 0; kb < C / 16; ++kb) {
+      const int4 wv = __ldg(reinterpret_cast<const int4*>(fc_wT) + static_cast<size_t>(kb) * 1024 + o);
+      const uint32_t ww[4] = {(uint32_t)wv.x, (uint32_t)wv.y, (uint32_t)wv.z, (uint32_t)wv.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        acc = __fmaf_rn(gq_s[kb * 16 + j], e4m3_to_float(static_cast<uint8_t>(ww[j >> 2] >> (8 * (j & 3)))), acc);
+    }
+    logits[static_cast<size_t>(n) * O + o] = __fmaf_rn(acc, fc_scale[o], fc_bias[o]);
   }
 }
 
@@ -671,14 +739,15 @@ int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
-  stem_s2d_kernel<int8_t, false><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f);
+  stem_s2d_kernel<int8_t, 0><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
-int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a) {
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a, int fp8) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
-  stem_s2d_kernel<float, true><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
+  if (fp8) stem_s2d_kernel<float, 2><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
+  else stem_s2d_kernel<float, 1><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
@@ -710,6 +779,14 @@ int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
+int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits) {
+  DLQ_ARG(ctx, in.C % 16 == 0 && O <= 1024, "gap/fc geometry");
+  gap_fc_e4m3_kernel<<<in.N, 512, in.C * sizeof(float), ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
+                                                                     inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
                const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits) {
   DLQ_ARG(ctx, in.C % 512 == 0 || in.C % 16 == 0, "gap channels");
@@ -738,6 +815,23 @@ int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int
   DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 15) == 0,
           "pointers must be 16-byte aligned");
   quantize_f32_i8_kernel<<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(x, n, inv_scale(scale), q);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_quantize_f32_e4m3(dlq_ctx* ctx, const float* x, size_t n, float scale, uint8_t* q) {
+  if (!ctx) return DLQ_ERR_ARG;
+  if (n == 0) return DLQ_OK;
+  DLQ_ARG(ctx, x && q && scale > 0.f, "null pointer or non-positive scale");
+  DLQ_ARG(ctx, (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(q) & 3) == 0, "pointers must be aligned");
+  quantize_f32_e4m3_kernel<<<grid_for(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(x, n, inv_scale(scale), q);
+  DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int dlq_dequantize_e4m3_f32(dlq_ctx* ctx, const uint8_t* q, size_t n, float scale, float* x) {
+  if (!ctx) return DLQ_ERR_ARG;
+  if (n == 0) return DLQ_OK;
+  DLQ_ARG(ctx, x && q, "null pointer");
+  dequantize_e4m3_f32_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(q, n, scale, x);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }

@@ -47,6 +47,9 @@ const char* dlq_version(void);
 /* q = clamp(rne(x * fp32(1/scale)), -128, 127) */
 int dlq_quantize_f32_i8(dlq_ctx* ctx, const float* x, size_t n, float scale, int8_t* q);
 int dlq_dequantize_i8_f32(dlq_ctx* ctx, const int8_t* q, size_t n, float scale, float* x);
+/* E4M3: q = e4m3_rn_satfinite(x * fp32(1/scale)); x' = float(q) * scale  (QUANT_SPEC 6) */
+int dlq_quantize_f32_e4m3(dlq_ctx* ctx, const float* x, size_t n, float scale, uint8_t* q);
+int dlq_dequantize_e4m3_f32(dlq_ctx* ctx, const uint8_t* q, size_t n, float scale, float* x);
 /* x[n,c,hw] = q * scale[c] */
 int dlq_dequantize_i8_f32_per_channel(dlq_ctx* ctx, const int8_t* q, int N, int C, int HW, const float* scale,
                                       float* x);
@@ -64,6 +67,13 @@ int dlq_conv_weights_pack(dlq_ctx* ctx, const float* w_oihw_host, int OC, int IC
 /* same from already-quantised int8 OIHW weights (HOST) */
 int dlq_conv_weights_pack_i8(dlq_ctx* ctx, const int8_t* wq_oihw_host, int OC, int IC, int kH, int kW, int sH,
                              int sW, int pH, int pW, dlq_conv_weights** out);
+/* FP8 (E4M3) variants, QUANT_SPEC section 6: per-output-channel scale = absmax / 448, round-to-nearest-even,
+ * saturate-to-finite; the conv runs on tcgen05 kind::f8f6f4 with FP32 accumulation. */
+int dlq_conv_weights_pack_fp8(dlq_ctx* ctx, const float* w_oihw_host, int OC, int IC, int kH, int kW, int sH, int sW,
+                              int pH, int pW, float* w_scale_host, dlq_conv_weights** out);
+int dlq_conv_weights_pack_e4m3(dlq_ctx* ctx, const uint8_t* wq_oihw_host, int OC, int IC, int kH, int kW, int sH,
+                               int sW, int pH, int pW, dlq_conv_weights** out);
+uint8_t dlq_f32_to_e4m3(float f); /* HOST helper: the conversion above for one value */
 void dlq_conv_weights_free(dlq_conv_weights* w);
 
 /* Fused epilogue, QUANT_SPEC §3 (requantisation-multiplier form; each line one binary32 rounding):
@@ -93,6 +103,12 @@ float dlq_res_mul(float s_r, float s_y);
  * (may be NULL; parity/debug).  OH/OW are returned like the reference's int& OH, int& OW. */
 int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
                   const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW);
+
+/* Same operator on E4M3 bytes (weights from dlq_conv_weights_pack_fp8/_e4m3): t = fmaf(acc_f32, alpha, beta) [+ residual],
+ * y = e4m3(relu ? max(t, 0) : t); acc_out receives the raw FP32 accumulators.  FP32 accumulation order inside the
+ * tensor core is unspecified, so parity with the oracle is by tolerance (QUANT_SPEC 6), not bit-exact. */
+int dlq_conv2d_fp8(dlq_ctx* ctx, const uint8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
+                   const dlq_epilogue* ep, uint8_t* y, float* acc_out, int* OH, int* OW);
 
 /* Native-layout variant (no NCHW transposes): activations as the library keeps them internally —
  * row-padded NHWC int8:  [PR zero rows][image 0: H rows of W*C bytes][PR zero rows][image 1] ...
@@ -160,6 +176,8 @@ typedef struct {
   const float* fc_w; /* [1000,512] */
   const float* fc_b; /* [1000] */
   float act_scale[DLQ_NUM_ACTS];
+  int fp8; /* 0: INT8 network (QUANT_SPEC 1-5).  1: E4M3 weights / activations, FP32 accumulation (QUANT_SPEC 6);
+            * act_scale then maps each tensor's absmax to 448 instead of 127 */
 } dlq_resnet18_weights;
 
 int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_batch, dlq_resnet18** out);
@@ -171,13 +189,13 @@ int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float
 /* int8 NCHW copy of an internal checkpoint of the LAST forward: "stem_pool","layer1".."layer4","gap"
  * (names as R/infer_e2e.cu:297-426 dumps them).  out is a device pointer. */
 int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);
-/* number of kernel launches one forward enqueues (for accounting) */
 /* Latency path (BASELINE config "batch 1"): capture one forward of batch N (x -> logits, both device pointers that
  * stay valid) into a CUDA graph once, then replay it with a single launch.  The reference instead pays ~45 launches,
  * allocations and weight uploads per image (R/infer_e2e.cu:230-441).  dlq_resnet18_graph_launch enqueues on the
  * context's stream and does not synchronise. */
 int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* logits);
 int dlq_resnet18_graph_launch(dlq_resnet18* m);
+/* number of kernel launches one forward enqueues (for accounting) */
 int dlq_resnet18_launches(const dlq_resnet18* m);
 /* one forward with a CUDA event between launches; ms[dlq_resnet18_launches()] receives each launch's device
  * time in order: quantise+s2d, stem conv, max-pool, per block conv1,[downsample],conv2, GAP+FC.  Synchronises.

@@ -503,6 +503,179 @@ void orc_resnet18_i8_forward(const orc_resnet18_i8* m, const float* x, int N, fl
   free(cur);
 }
 
+/* ============================================================ FP8 (E4M3) path — spec/QUANT_SPEC.md section 6 */
+uint8_t orc_f32_to_e4m3(float f) {
+  const uint8_t sign = signbit(f) ? 0x80 : 0x00;
+  if (isnan(f)) return (uint8_t)(sign | 0x7F);
+  const float a = fabsf(f);
+  if (a >= 448.0f) return (uint8_t)(sign | 0x7E);            /* saturate to the largest finite value */
+  if (a < 0.015625f) {                                       /* below 2^-6: subnormals, multiples of 2^-9 */
+    const int q = (int)nearbyintf(a * 512.0f);               /* 0..8; 8 is the smallest normal (same encoding) */
+    return (uint8_t)(sign | q);
+  }
+  int e;
+  const float fr = frexpf(a, &e);                            /* a = fr * 2^e, fr in [0.5,1) */
+  int ex = e - 1;
+  int m = (int)nearbyintf((2.0f * fr - 1.0f) * 8.0f);        /* 3 mantissa bits, round half to even */
+  if (m == 8) { m = 0; ++ex; }
+  if (ex > 8 || (ex == 8 && m == 7)) return (uint8_t)(sign | 0x7E);
+  return (uint8_t)(sign | ((ex + 7) << 3) | m);
+}
+
+float orc_e4m3_to_f32(uint8_t b) {
+  const int sgn = b >> 7, ex = (b >> 3) & 0xF, m = b & 7;
+  float v;
+  if (ex == 0xF && m == 7) v = NAN;
+  else if (ex == 0) v = ldexpf((float)m, -9);
+  else v = ldexpf(1.0f + (float)m / 8.0f, ex - 7);
+  return sgn ? -v : v;
+}
+
+void orc_quantize_f32_e4m3(const float* x, size_t n, float inv_s, uint8_t* q) {
+  for (size_t i = 0; i < n; ++i) q[i] = orc_f32_to_e4m3(x[i] * inv_s);
+}
+void orc_dequantize_e4m3_f32(const uint8_t* q, size_t n, float s, float* x) {
+  for (size_t i = 0; i < n; ++i) x[i] = orc_e4m3_to_f32(q[i]) * s;
+}
+void orc_quantize_weights_per_channel_e4m3(const float* w, int OC, int K, uint8_t* q, float* s) {
+  for (int o = 0; o < OC; ++o) {
+    float am = 0.f;
+    for (int k = 0; k < K; ++k) am = fmaxf(am, fabsf(w[(size_t)o * K + k]));
+    const float sc = am > 0.f ? (float)((double)am / 448.0) : 1.0f;
+    s[o] = sc;
+    const float inv = orc_inv_scale(sc);
+    for (int k = 0; k < K; ++k) q[(size_t)o * K + k] = orc_f32_to_e4m3(w[(size_t)o * K + k] * inv);
+  }
+}
+
+static uint8_t epilogue_e4m3(float acc, float alpha, float beta, int has_res, uint8_t r, float res_mul, int relu) {
+  float t = fmaf(acc, alpha, beta);
+  if (has_res) t = fmaf(orc_e4m3_to_f32(r), res_mul, t);
+  if (relu && t < 0.f) t = 0.f;
+  return orc_f32_to_e4m3(t);
+}
+
+void orc_conv2d_e4m3(const uint8_t* x, int N, int C, int H, int W, const uint8_t* w, int OC, int kH, int kW, int sH,
+                     int sW, int pH, int pW, const orc_epilogue* ep, float* acc_out, uint8_t* y) {
+  const int OH = (H + 2 * pH - kH) / sH + 1, OW = (W + 2 * pW - kW) / sW + 1;
+  const int K = C * kH * kW;
+  float lut[256];
+  for (int i = 0; i < 256; ++i) lut[i] = orc_e4m3_to_f32((uint8_t)i);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int n = 0; n < N; ++n)
+    for (int oc = 0; oc < OC; ++oc) {
+      const uint8_t* xn = x + (size_t)n * C * H * W;
+      const uint8_t* wr = w + (size_t)oc * K;
+      const size_t obase = ((size_t)n * OC + oc) * OH * OW;
+      for (int oh = 0; oh < OH; ++oh)
+        for (int ow = 0; ow < OW; ++ow) {
+          double acc = 0.0;
+          for (int kh = 0; kh < kH; ++kh) {
+            const int ih = oh * sH - pH + kh;
+            if (ih < 0 || ih >= H) continue;
+            for (int kw = 0; kw < kW; ++kw) {
+              const int iw = ow * sW - pW + kw;
+              if (iw < 0 || iw >= W) continue;
+              const uint8_t* xp = xn + (size_t)ih * W + iw;
+              const uint8_t* wp = wr + kh * kW + kw;
+              for (int c = 0; c < C; ++c)
+                acc += (double)lut[xp[(size_t)c * H * W]] * (double)lut[wp[c * kH * kW]];
+            }
+          }
+          const size_t o = obase + (size_t)oh * OW + ow;
+          if (acc_out) acc_out[o] = (float)acc;
+          if (y && ep)
+            y[o] = epilogue_e4m3((float)acc, ep->alpha[oc], ep->beta[oc], ep->residual != NULL,
+                                 ep->residual ? (uint8_t)ep->residual[o] : 0, ep->res_mul, ep->relu);
+        }
+    }
+}
+
+void orc_gap_e4m3(const uint8_t* x, int N, int C, int H, int W, float scale_over_hw, float inv_out_scale, uint8_t* y) {
+  const int HW = H * W;
+  for (int nc = 0; nc < N * C; ++nc) {
+    double sum = 0.0;
+    for (int i = 0; i < HW; ++i) sum += (double)orc_e4m3_to_f32(x[(size_t)nc * HW + i]);
+    y[nc] = orc_f32_to_e4m3(((float)sum * scale_over_hw) * inv_out_scale);
+  }
+}
+
+void orc_fc_e4m3(const uint8_t* g, const uint8_t* w, const float* w_scale_times_g, const float* bias, int N, int O,
+                 int I, float* logits) {
+  for (int n = 0; n < N; ++n)
+    for (int o = 0; o < O; ++o) {
+      double acc = 0.0;
+      for (int k = 0; k < I; ++k) acc += (double)orc_e4m3_to_f32(w[(size_t)o * I + k]) * (double)orc_e4m3_to_f32(g[(size_t)n * I + k]);
+      logits[(size_t)n * O + o] = fmaf((float)acc, w_scale_times_g[o], bias[o]);
+    }
+}
+
+static uint8_t* convq8(const orc_convq* p, const uint8_t* x, int N, int H, int W, const uint8_t* res, float res_mul,
+                       int relu, int* OH, int* OW) {
+  *OH = (H + 2 * p->pad - p->k) / p->stride + 1;
+  *OW = (W + 2 * p->pad - p->k) / p->stride + 1;
+  uint8_t* y = (uint8_t*)malloc((size_t)N * p->oc * (*OH) * (*OW));
+  orc_epilogue ep = {p->alpha, p->beta, (const int8_t*)res, res_mul, relu};
+  orc_conv2d_e4m3(x, N, p->ic, H, W, (const uint8_t*)p->w, p->oc, p->k, p->k, p->stride, p->stride, p->pad, p->pad, &ep,
+                  NULL, y);
+  return y;
+}
+
+/* Whole network in E4M3; wiring identical to orc_resnet18_i8_forward.  The max-pool runs on the bytes as signed
+ * int8: its input is a ReLU output (codes 0x00..0x7E), on which the E4M3 order and the byte order agree. */
+void orc_resnet18_fp8_forward(const orc_resnet18_i8* m, const float* x, int N, float* logits, orc_checkpoints_i8* ck) {
+  const float* S = m->act_scale;
+  int H = 224, W = 224, OH, OW;
+  uint8_t* qx = (uint8_t*)malloc((size_t)N * 3 * H * W);
+  orc_quantize_f32_e4m3(x, (size_t)N * 3 * H * W, orc_inv_scale(S[ORC_ACT_INPUT]), qx);
+  uint8_t* y0 = convq8(&m->convs[0], qx, N, H, W, NULL, 0.f, 1, &OH, &OW);
+  free(qx);
+  const int PH = (OH + 2 - 3) / 2 + 1, PW = (OW + 2 - 3) / 2 + 1;
+  uint8_t* cur = (uint8_t*)malloc((size_t)N * 64 * PH * PW);
+  orc_maxpool3x3s2p1_i8((const int8_t*)y0, N, 64, OH, OW, (int8_t*)cur);
+  free(y0);
+  H = PH;
+  W = PW;
+  if (ck && ck->stem_pool) memcpy(ck->stem_pool, cur, (size_t)N * 64 * H * W);
+  float s_cur = S[ORC_ACT_STEM];
+  int C = 64;
+  for (int b = 0; b < ORC_NUM_BLOCKS; ++b) {
+    const orc_convq* c1 = &m->convs[1 + 3 * b];
+    const orc_convq* c2 = &m->convs[2 + 3 * b];
+    const orc_convq* ds = &m->convs[3 + 3 * b];
+    const float s_ds = S[ORC_ACT_BLOCK0 + 3 * b + 1], s_out = S[ORC_ACT_BLOCK0 + 3 * b + 2];
+    int H1, W1, H2, W2;
+    uint8_t* t1 = convq8(c1, cur, N, H, W, NULL, 0.f, 1, &H1, &W1);
+    uint8_t* t2;
+    if (ds->w) {
+      int Hd, Wd;
+      uint8_t* sk = convq8(ds, cur, N, H, W, NULL, 0.f, 0, &Hd, &Wd);
+      t2 = convq8(c2, t1, N, H1, W1, sk, orc_res_mul(s_ds, s_out), 1, &H2, &W2);
+      free(sk);
+    } else {
+      t2 = convq8(c2, t1, N, H1, W1, cur, orc_res_mul(s_cur, s_out), 1, &H2, &W2);
+    }
+    free(t1);
+    free(cur);
+    cur = t2;
+    s_cur = s_out;
+    H = H2;
+    W = W2;
+    C = c2->oc;
+    if (ck) {
+      int8_t* dst = (b == 1) ? ck->layer1 : (b == 3) ? ck->layer2 : (b == 5) ? ck->layer3 : (b == 7) ? ck->layer4 : NULL;
+      if (dst) memcpy(dst, cur, (size_t)N * C * H * W);
+    }
+  }
+  uint8_t* g = (uint8_t*)malloc((size_t)N * C);
+  const float s_over_hw = (float)((double)s_cur / (double)(H * W));
+  orc_gap_e4m3(cur, N, C, H, W, s_over_hw, orc_inv_scale(S[ORC_ACT_GAP]), g);
+  if (ck && ck->gap) memcpy(ck->gap, g, (size_t)N * C);
+  orc_fc_e4m3(g, (const uint8_t*)m->fc_w, m->fc_scale, m->fc_b, N, 1000, C, logits);
+  free(g);
+  free(cur);
+}
+
 /* ============================================================ MNIST MLP forward (config #1) */
 /* MN/v3.c:125-134 matmul_a_b (accumulates through memory in l order; plain mul+add, no FMA since
  * this file is built with -ffp-contract=off like `gcc -O2` on x86-64 without -mfma),

@@ -146,6 +146,24 @@ typedef struct {
 void orc_resnet18_i8_forward(const orc_resnet18_i8* m, const float* x, int N, float* logits,
                              orc_checkpoints_i8* ck);
 
+/* ---------------------------------------------------------------- FP8 (E4M3) path, spec/QUANT_SPEC.md section 6
+ * PARITY UNPINNED by the reference (it has no quantised code).  E4M3 = 1-4-3, bias 7, max 448, 0x7F/0xFF = NaN;
+ * float -> E4M3 rounds to nearest even and saturates to +-448.  Products are accumulated in DOUBLE here (the
+ * tensor core's fp32 accumulation order is unspecified), so GPU parity is by tolerance. */
+uint8_t orc_f32_to_e4m3(float f);
+float orc_e4m3_to_f32(uint8_t b);
+void orc_quantize_f32_e4m3(const float* x, size_t n, float inv_s, uint8_t* q);
+void orc_dequantize_e4m3_f32(const uint8_t* q, size_t n, float s, float* x);
+void orc_quantize_weights_per_channel_e4m3(const float* w, int OC, int K, uint8_t* q, float* s);
+/* residual in ep is read as E4M3 bytes; acc_out = (float)double_accumulator */
+void orc_conv2d_e4m3(const uint8_t* x, int N, int C, int H, int W, const uint8_t* w, int OC, int kH, int kW, int sH,
+                     int sW, int pH, int pW, const orc_epilogue* ep, float* acc_out, uint8_t* y);
+void orc_gap_e4m3(const uint8_t* x, int N, int C, int H, int W, float scale_over_hw, float inv_out_scale, uint8_t* y);
+void orc_fc_e4m3(const uint8_t* g, const uint8_t* w, const float* w_scale_times_g, const float* bias, int N, int O,
+                 int I, float* logits);
+/* same model struct as the INT8 network: weight bytes are E4M3 codes, act_scale maps absmax to 448 */
+void orc_resnet18_fp8_forward(const orc_resnet18_i8* m, const float* x, int N, float* logits, orc_checkpoints_i8* ck);
+
 /* ---------------------------------------------------------------- MNIST MLP forward (config #1) */
 /* restatement of CUDA/MNIST_on_GPU/v3.c:108-215 (forward only) */
 void orc_mnist_mlp_forward(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,

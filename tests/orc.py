@@ -67,6 +67,10 @@ def lib() -> C.CDLL:
         _lib.orc_num_threads.restype = C.c_int
         _lib.orc_res_mul.restype = C.c_float
         _lib.orc_res_mul.argtypes = [C.c_float, C.c_float]
+        _lib.orc_f32_to_e4m3.restype = C.c_uint8
+        _lib.orc_f32_to_e4m3.argtypes = [C.c_float]
+        _lib.orc_e4m3_to_f32.restype = C.c_float
+        _lib.orc_e4m3_to_f32.argtypes = [C.c_uint8]
     return _lib
 
 
@@ -244,6 +248,61 @@ def conv2d_i8(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_mul=
     return acc, y
 
 
+# ------------------------------------------------------------------ FP8 (E4M3) ops, QUANT_SPEC section 6
+def f32_to_e4m3(v: float) -> int:
+    return int(lib().orc_f32_to_e4m3(C.c_float(v)))
+
+
+def e4m3_table() -> np.ndarray:
+    """float value of each of the 256 E4M3 codes"""
+    return np.array([lib().orc_e4m3_to_f32(C.c_uint8(i)) for i in range(256)], dtype=np.float32)
+
+
+def quantize_e4m3(x, scale):
+    x = f32(x)
+    q = np.empty(x.shape, dtype=np.uint8)
+    lib().orc_quantize_f32_e4m3(_p(x), C.c_size_t(x.size), C.c_float(inv_scale(scale)), _p(q))
+    return q
+
+
+def dequantize_e4m3(q, scale):
+    q = np.ascontiguousarray(q, dtype=np.uint8)
+    x = np.empty(q.shape, dtype=np.float32)
+    lib().orc_dequantize_e4m3_f32(_p(q), C.c_size_t(q.size), C.c_float(scale), _p(x))
+    return x
+
+
+def quantize_weights_e4m3(w):
+    w = f32(w)
+    oc = w.shape[0]
+    k = w.size // oc
+    q = np.empty(w.shape, dtype=np.uint8)
+    s = np.empty(oc, dtype=np.float32)
+    lib().orc_quantize_weights_per_channel_e4m3(_p(w), oc, k, _p(q), _p(s))
+    return q, s
+
+
+def conv2d_e4m3(x, wq, stride, pad, alpha=None, beta=None, residual=None, res_mul=0.0, relu=False, want_acc=True):
+    """x, wq, residual: E4M3 codes (uint8); returns (acc float32 NCHW or None, y uint8 NCHW or None)"""
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    wq = np.ascontiguousarray(wq, dtype=np.uint8)
+    n, c, h, w = x.shape
+    oc, _, kh, kw = wq.shape
+    oh, ow = (h + 2 * pad - kh) // stride + 1, (w + 2 * pad - kw) // stride + 1
+    acc = np.empty((n, oc, oh, ow), dtype=np.float32) if want_acc else None
+    y, ep = None, None
+    keep = []
+    if alpha is not None:
+        y = np.empty((n, oc, oh, ow), dtype=np.uint8)
+        a, b = f32(alpha), f32(beta)
+        r = None if residual is None else np.ascontiguousarray(residual, dtype=np.uint8)
+        keep = [a, b, r]
+        ep = Epilogue(_p(a), _p(b), _p(r), res_mul, int(relu))
+    lib().orc_conv2d_e4m3(_p(x), n, c, h, w, _p(wq), oc, kh, kw, stride, stride, pad, pad,
+                          C.byref(ep) if ep is not None else None, _p(acc), _p(y))
+    return acc, y
+
+
 def add_requant_i8(y, y_scale, x, x_scale, relu, out_scale):
     y = np.ascontiguousarray(y, dtype=np.int8).copy()
     x = np.ascontiguousarray(x, dtype=np.int8)
@@ -339,8 +398,16 @@ def calibrate(weights, x_calib) -> np.ndarray:
     return (am.astype(np.float64) / 127.0).astype(np.float32)
 
 
+def fp8_act_scales(int8_scales) -> np.ndarray:
+    """E4M3 activation scales from the INT8 calibration: the same absmax, mapped to 448 instead of 127"""
+    return (np.asarray(int8_scales, dtype=np.float64) * 127.0 / 448.0).astype(np.float32)
+
+
 class I8Model:
     """INT8 oracle model: quantised weights + folded constants from fp32 weights and activation scales."""
+    QUANT_W = staticmethod(lambda w: quantize_weights(w))
+    FORWARD = "orc_resnet18_i8_forward"
+    CK_DTYPE = np.int8
 
     def __init__(self, weights: Dict[str, np.ndarray], act_scale):
         geo, keys = _geometry()
@@ -365,13 +432,13 @@ class I8Model:
                 continue
             ic, oc, k, st, p = geo[idx]
             wk, bn = keys[idx]
-            q, sw = quantize_weights(weights[wk])
+            q, sw = self.QUANT_W(weights[wk])
             a, bt = fold_bn(weights[bn + ".weight"], weights[bn + ".bias"], weights[bn + ".running_mean"],
                             weights[bn + ".running_var"], sw, float(s_in[idx]), float(s_out[idx]))
             self.wq[idx], self.alpha[idx], self.beta[idx], self.s_w[idx] = q, a, bt, sw
             cq.ic, cq.oc, cq.k, cq.stride, cq.pad = ic, oc, k, st, p
             cq.w, cq.alpha, cq.beta = q.ctypes.data, a.ctypes.data, bt.ctypes.data
-        self.fc_q, fc_sw = quantize_weights(weights["fc.weight"])
+        self.fc_q, fc_sw = self.QUANT_W(weights["fc.weight"])
         self.fc_scale = (np.float64(S[ACT_GAP]) * fc_sw.astype(np.float64)).astype(np.float32)
         self.fc_b = f32(weights["fc.bias"])
         self.s.fc_w, self.s.fc_scale, self.s.fc_b = self.fc_q.ctypes.data, self.fc_scale.ctypes.data, self.fc_b.ctypes.data
@@ -386,8 +453,16 @@ class I8Model:
             shapes = {"stem_pool": (n, 64, 56, 56), "layer1": (n, 64, 56, 56), "layer2": (n, 128, 28, 28),
                       "layer3": (n, 256, 14, 14), "layer4": (n, 512, 7, 7), "gap": (n, 512)}
             for k, shp in shapes.items():
-                out[k] = np.empty(shp, dtype=np.int8)
+                out[k] = np.empty(shp, dtype=self.CK_DTYPE)
                 setattr(ck, k, out[k].ctypes.data)
-        lib().orc_resnet18_i8_forward(C.byref(self.s), _p(x), n, _p(logits), C.byref(ck))
+        getattr(lib(), self.FORWARD)(C.byref(self.s), _p(x), n, _p(logits), C.byref(ck))
         out["logits"] = logits
         return out
+
+
+class FP8Model(I8Model):
+    """E4M3 oracle model (QUANT_SPEC section 6): same wiring, E4M3 codes, double-accumulated products.
+    act_scale: per-tensor scales mapping absmax to 448 (fp8_act_scales of the INT8 calibration)."""
+    QUANT_W = staticmethod(lambda w: quantize_weights_e4m3(w))
+    FORWARD = "orc_resnet18_fp8_forward"
+    CK_DTYPE = np.uint8
