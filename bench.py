@@ -59,8 +59,42 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index = index
         self.p = None
+        self.thread = None
+        self.samples = []
+        self.stop_flag = False
+
+    # NVML in-process sampling (every ~2 ms: the timed region of a short run lasts tens of milliseconds, too short
+    # for `nvidia-smi -lms`); the nvidia-smi subprocess is the fallback
+    def _nvml_loop(self, handle, nv):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(sm), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.stop_flag = False
+            self.samples = []
+            self.thread = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-i", str(self.index), "-lms", "100"],
@@ -69,6 +103,18 @@ class ClockSampler:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.samples:
+                bits = 0
+                for _, r in self.samples:
+                    bits |= r
+                names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+                return {"sm_mhz": statistics.median([c for c, _ in self.samples]), "sm_max_mhz": self.max_mhz,
+                        "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(self.samples),
+                        "how": "NVML, sampled every 2 ms during the timed region"}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)

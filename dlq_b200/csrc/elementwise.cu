@@ -25,6 +25,23 @@ void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes) {
   return ctx->scratch[slot];
 }
 
+// launch with cudaLaunchAttributeProgrammaticStreamSerialization (the kernel must call pdl_wait() before it reads
+// anything a previous kernel wrote)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("DLQ_DBG_NO_PDL") ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static inline int grid_for(dlq_ctx* ctx, size_t work_items, int threads, int max_waves = 8) {
   const size_t blocks = (work_items + threads - 1) / threads;
   const size_t cap = static_cast<size_t>(ctx->num_sms) * max_waves;
@@ -186,6 +203,8 @@ template <typename T, int QMODE>
 __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
                                 float inv_s) {
   const int H2 = H / 2, W2 = W / 2, WP = W2 + 3;
+  pdl_launch_dependents();
+  pdl_wait();          // (programmatic dependent launch: the previous kernel on the stream may still be draining)
   const size_t total = static_cast<size_t>(N) * H2 * W2;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -400,8 +419,10 @@ maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     fence_mbar_init();
+    pdl_launch_dependents();
   }
   __syncthreads();
+  pdl_wait();          // the stem conv's output must be complete before the first slab load
   // slab of tile t: input rows [2*oh0 - 1, 2*oh0 + 2*TR - 1] clipped to the image; slot r of the buffer holds row 2*oh0-1+r
   auto issue = [&](int t, int stage) {
     const int n = t / tiles_per_img, oh0 = (t - n * tiles_per_img) * TR;
@@ -501,7 +522,7 @@ __global__ void maxpool_nchw_i8_kernel(const int8_t* __restrict__ x, int8_t* __r
 // once per CTA, each warp producing one output row for all IMG images with dp4a + warp shuffles.
 // (semantics: K/gap_global.cu:10-32 mean, R/infer_e2e.cu:206-219 FC + bias; arithmetic QUANT_SPEC §5)
 // ------------------------------------------------------------------------------------------------
-constexpr int kGapImgs = 4;
+constexpr int kGapImgs = 2;
 constexpr int kGapParts = 4;
 __global__ void __launch_bounds__(512)
 gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
@@ -513,6 +534,7 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
   const int n0 = blockIdx.x * kGapImgs;
   const int nimg = min(kGapImgs, N - n0);
   const int HW = H * W;
+  pdl_wait();
   {
     // phase 1a: thread = (image, pixel partition, 16-channel group); 16-byte loads, all independent
     const int im = threadIdx.x >> 7, part = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
@@ -746,9 +768,9 @@ int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, cons
 int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a, int fp8) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
-  if (fp8) stem_s2d_kernel<float, 2><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
-  else stem_s2d_kernel<float, 1><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, inv_s);
-  DLQ_CUDA(ctx, cudaGetLastError());
+  const int grid = grid_for(ctx, total, 256);
+  if (fp8) DLQ_CUDA(ctx, launch_pdl(stem_s2d_kernel<float, 2>, dim3(grid), dim3(256), 0, ctx->stream, x, a.ptr, N, H, W, a.PR, inv_s));
+  else DLQ_CUDA(ctx, launch_pdl(stem_s2d_kernel<float, 1>, dim3(grid), dim3(256), 0, ctx->stream, x, a.ptr, N, H, W, a.PR, inv_s));
   return DLQ_OK;
 }
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
@@ -767,9 +789,8 @@ int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
       }
       const int n_tiles = in.N * ((out.H + TR - 1) / TR);
       const int grid = std::max(1, std::min(n_tiles, ctx->num_sms));
-      maxpool_rows_kernel<TR><<<grid, 256, smem, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR, out.H,
-                                                                out.W, out.PR);
-      DLQ_CUDA(ctx, cudaGetLastError());
+      DLQ_CUDA(ctx, launch_pdl(maxpool_rows_kernel<TR>, dim3(grid), dim3(256), smem, ctx->stream,
+                               static_cast<const int8_t*>(in.ptr), out.ptr, in.N, in.H, in.W, in.C, in.PR, out.H, out.W, out.PR));
       return DLQ_OK;
     }
   }
@@ -793,9 +814,8 @@ int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_s
   DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
   const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
   const size_t gap_smem = static_cast<size_t>(kGapImgs) * kGapParts * in.C * 4 + static_cast<size_t>(kGapImgs) * in.C;
-  gap_fc_kernel<<<blocks, 512, gap_smem, ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
-                                                               inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits);
-  DLQ_CUDA(ctx, cudaGetLastError());
+  DLQ_CUDA(ctx, launch_pdl(gap_fc_kernel, dim3(blocks), dim3(512), gap_smem, ctx->stream, static_cast<const int8_t*>(in.ptr),
+                           in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits));
   return DLQ_OK;
 }
 
