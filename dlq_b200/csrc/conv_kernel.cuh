@@ -42,6 +42,7 @@ namespace dlq {
 
 constexpr int kMaxSteps = 40;    // K steps (tap x channel-block) per conv
 constexpr int kMaxPlanes = 4;
+constexpr uint16_t kStepSecond = 0x8000;
 constexpr int kTileM = 128;
 constexpr int kEpiStageRow = 64;                       // bytes per staged row; 16-byte chunk q of row r lives at chunk
                                                        // q ^ ((r >> 1) & 3): conflict-free both row-per-lane and coalesced
@@ -76,7 +77,8 @@ struct ConvKernelParams {
   int16_t sub_step0[17];  //   first K step of each sub-patch (sub_step0[n_sub] = n_steps)
   // K steps
   int n_steps;
-  uint16_t step_a16[kMaxSteps];   // A view offset of each step inside its sub-patch, in 16-byte units (tap shift * ROWB / 16)
+  uint16_t step_a16[kMaxSteps];   // A view offset of each step inside its sub-patch, in 16-byte units (tap shift * ROWB / 16);
+                                  // bit 15 (kStepSecond): the step belongs to the fused second conv (see `fused`)
   int a_stages, b_stages, acc_stages;
   int b_resident;         // 1: all weight steps stay in smem (b_stages == n_steps), loaded once per CTA (needs n_tiles == 1)
   int w_rows;             // weight rows (output channels) each CTA loads per step: n_tile, or n_tile/2 in a pair
@@ -91,6 +93,17 @@ struct ConvKernelParams {
   int8_t* out;            // row-padded NHWC int8
   int out_PR;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
+  // Fused second conv (ResNet downsample blocks, R/infer_e2e.cu:181-196): the 1x1/s2 shortcut conv reads exactly the
+  // A view of the 3x3/s2 conv's centre tap, so both run from ONE patch load: steps flagged kStepSecond multiply that
+  // view with the shortcut's weights into a second accumulator block (TMEM columns + MT*n_tile), and the epilogue
+  // writes it through its own alpha/beta/ReLU/output.  Requires MT == 1 and no residual.
+  int fused;
+  int first_second_step;  // index of the first kStepSecond step (overwrites the second accumulator)
+  const float* alpha2;
+  const float* beta2;
+  int relu2;
+  int8_t* out2;
+  int out2_PR;
   uint32_t wp_magic, pv_magic;   // floor(2^32/d)+1 for d = Wp, Pv (exact for positions < 2^24); 0 = use hardware division
   int dbg;                // tuning experiments only: 1 = skip the epilogue, 2 = skip MMA issue, 4 = skip A loads
   long long* dbg_times;   // optional [gridDim.x][8] cycle counters (tuning): see conv_plan.cu
@@ -117,6 +130,8 @@ struct IssuerCtx {
   uint32_t tmem_base, acc_cols, n_tile;
   int n_sub, a_stages, b_stages, acc_stages, Wp, super_stride, n_tiles;
   int it_begin, it_end, it_stride;
+  int fused, first_second_step;
+  uint32_t second_off;          // accumulator column offset of the fused second conv
   uint32_t tile_off16;          // this issuer's first tile, in 16-byte units down the patch
   uint32_t d_off;               // this issuer's first accumulator column offset
   bool leader;
@@ -216,7 +231,21 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, false, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          const uint32_t so = c.step_a16[k];
+          if (c.fused && (so & kStepSecond)) {
+            // fused second conv: all K slices from the first issuer (no cross-issuer ordering on its accumulator),
+            // the first such step overwrites
+            if (KSEL != 2 && !(c.dbg & 2)) {
+              constexpr int K32 = ROWB / 32;
+#pragma unroll
+              for (int kk = 0; kk < K32; ++kk)
+                umma_issue<TWO, FP8>(d0 + c.second_off, (static_cast<uint64_t>(a_hi) << 32) | (a_base + (so & 0x7FFFu) + 2u * kk),
+                                     (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc,
+                                     (k == c.first_second_step && kk == 0) ? 0u : 1u);
+            }
+          } else if (!(c.dbg & 2)) {
+            issue_step<ROWB, MYMT, false, TWO, KSEL, FP8>(a_hi, b_hi, a_base + so, b_lo, d0, c.n_tile, idesc);
+          }
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
@@ -252,6 +281,8 @@ struct EpiCtx {
   uint8_t* slots;          // this warp's staging: [2][32 rows][kEpiStageRow]
   int lane, crow, cq;      // coalesced phase: row within a group of 8, 16-byte quarter
   int out_pitch, res_pitch, n0;
+  int8_t* out;             // output tensor of the current unit (the fused second conv has its own)
+  int out_PR;
   uint32_t relu_mask;      // 0xFFFFFFFF: ReLU (negative bytes -> 0), 0: none
   float res_mul;
 };
@@ -318,7 +349,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   for (int u = 0; u < NU; ++u) {
     int n, r, x;
     valid[u] = decode_pos(p, g_own[u], n, r, x);
-    opix[u] = valid[u] ? static_cast<uint32_t>((p.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
+    opix[u] = valid[u] ? static_cast<uint32_t>((e.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
     dpix[u] = ACC_OUT ? (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x : 0;
   }
   uint8_t* my_row[NU];    // own staged row (row = lane); chunk q sits at my_row + ((q ^ my_swz) << 4)
@@ -409,7 +440,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
     }
   }
   __syncwarp();
-  if (p.out) {
+  if (e.out) {
     // all shuffles, then all (unconditional) staged reads, then the predicated stores: no serialised
     // shuffle -> load -> store chains
     uint32_t op[NU][4];
@@ -428,7 +459,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (op[u][j] != kInvalidPix)
-          *(reinterpret_cast<int4*>(p.out + static_cast<size_t>(op[u][j]) * p.OC + e.n0 + c0[u]) + e.cq) = val[u][j];
+          *(reinterpret_cast<int4*>(e.out + static_cast<size_t>(op[u][j]) * p.OC + e.n0 + c0[u]) + e.cq) = val[u][j];
   }
   __syncwarp();
 }
@@ -451,7 +482,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   uint8_t* sB = sA + static_cast<size_t>(p.a_stages) * a_stage_bytes;
   float* s_alpha = reinterpret_cast<float*>(sB + static_cast<size_t>(p.b_stages) * b_stage_bytes);
   float* s_beta = s_alpha + p.OC;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + p.OC);              // [epilogue warps][2 slots][kEpiStageBytes]
+  float* s_alpha2 = s_beta + p.OC;                                           // (fused second conv)
+  float* s_beta2 = s_alpha2 + p.OC;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta2 + p.OC);             // [epilogue warps][2 slots][kEpiStageBytes]
   uint16_t* s_step_a16 = reinterpret_cast<uint16_t*>(s_stage + 16 * kEpiStageBytes);   // [kMaxSteps]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_step_a16 + kMaxSteps + 8);
   uint64_t* a_full = bars;
@@ -476,7 +509,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
   const int gid = static_cast<int>(blockIdx.x) / ncta;          // CTA (or pair) index
   const int G = static_cast<int>(gridDim.x) / ncta;             // CTAs (or pairs) in the grid
-  const uint32_t acc_cols = static_cast<uint32_t>(p.MT) * p.n_tile;   // TMEM columns per accumulator stage
+  const uint32_t acc_cols = static_cast<uint32_t>(p.MT) * p.n_tile * (p.fused ? 2u : 1u);   // TMEM columns per accumulator stage
   uint32_t tmem_cols = 32;
   while (tmem_cols < acc_cols * p.acc_stages) tmem_cols <<= 1;
 
@@ -503,6 +536,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   for (int i = threadIdx.x; i < p.OC; i += blockDim.x) {
     s_alpha[i] = p.alpha ? p.alpha[i] : 1.f;
     s_beta[i] = p.beta ? p.beta[i] : 0.f;
+    if (p.fused) { s_alpha2[i] = p.alpha2[i]; s_beta2[i] = p.beta2[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -586,6 +620,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     c.n_sub = p.n_sub; c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.acc_stages = p.acc_stages;
     c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles;
     c.it_begin = gid; c.it_end = p.n_items; c.it_stride = G;
+    c.fused = p.fused; c.first_second_step = p.first_second_step;
+    c.second_off = static_cast<uint32_t>(p.MT) * p.n_tile;
     const int issuer = (warp == 1) ? 0 : 1;
     const int my_mt = k_split ? 1 : p.MT / n_issuers;   // tiles this issuer owns: [issuer*my_mt, +my_mt)
     c.tile_off16 = k_split ? 0u : static_cast<uint32_t>(issuer * my_mt) * TILE16;
@@ -617,15 +653,17 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const int row = quarter * 32 + lane;                // accumulator row within the tile
     const bool has_res = p.residual != nullptr;
     const int cblocks = p.n_tile >> 6;
-    const int n_units = p.MT * cblocks;
+    const int units1 = p.MT * cblocks;                   // units of the (first) conv; the fused second conv adds as many
+    const int n_units = units1 * (p.fused ? 2 : 1);
     const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per item: grp, grp + n_groups, ...
-    const int upp = p.acc_out ? 1 : 2;                  // units per pass (raw-accumulator output: one at a time)
+    const int upp = (p.acc_out || p.fused) ? 1 : 2;     // units per pass (raw-accumulator output / fused second conv: one at a time)
     const int n_pairs = (upw + upp - 1) / upp;
     EpiCtx e;
     e.s_alpha = s_alpha; e.s_beta = s_beta;
     e.slots = s_stage + ew * 2 * kEpiStageBytes;
     e.lane = lane; e.crow = lane >> 2; e.cq = lane & 3;
     e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = 0;
+    e.out = p.out; e.out_PR = p.out_PR;
     e.relu_mask = p.relu ? 0xFFFFFFFFu : 0u;
     e.res_mul = p.res_mul;
     // global position of this lane's row in tile mt of super-tile st (rows past the super-tile's own positions
@@ -668,18 +706,26 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       for (int pi = 0; pi < np; ++pi) {
         uint32_t taddr[2];
         int c0[2], g_own[2];
-        const int nu = (2 * pi + 1 < upw && !p.acc_out) ? 2 : 1;
+        const int nu = (upp == 2 && 2 * pi + 1 < upw) ? 2 : 1;
         e.n0 = nt * p.n_tile;
-        e.s_alpha = s_alpha + e.n0;
-        e.s_beta = s_beta + e.n0;
+        // (fused launches process one unit per pass, so a pass never mixes the two convs)
+        const int unit0 = grp + upp * pi * n_groups;
+        const bool second = unit0 >= units1;
+        e.s_alpha = (second ? s_alpha2 : s_alpha) + e.n0;
+        e.s_beta = (second ? s_beta2 : s_beta) + e.n0;
+        e.out = second ? p.out2 : p.out;
+        e.out_PR = second ? p.out2_PR : p.out_PR;
+        e.out_pitch = p.Ho + e.out_PR;
+        e.relu_mask = (second ? p.relu2 : p.relu) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
+          int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
+          if (second) unit -= units1;
           const int mt = unit / cblocks, cb = unit - mt * cblocks;
           c0[u] = cb << 6;
           g_own[u] = own_pos(st, mt);
-          taddr[u] = tmem_base + cs * acc_cols + static_cast<uint32_t>(mt) * p.n_tile + c0[u] +
-                     (static_cast<uint32_t>(quarter * 32) << 16);
+          taddr[u] = tmem_base + cs * acc_cols + (second ? static_cast<uint32_t>(p.MT) * p.n_tile : 0u) +
+                     static_cast<uint32_t>(mt) * p.n_tile + c0[u] + (static_cast<uint32_t>(quarter * 32) << 16);
         }
         const bool last = pi == np - 1;
         if (has_res) {

@@ -36,6 +36,7 @@ struct StepDesc {
   int kh, kw;  // filter tap (stem: kh = row block a, kw = column pair bp)
   int kb;      // channel block
   int da, db;  // tap shift in patch rows / columns
+  int second = 0;  // 1: step of the fused 1x1 shortcut conv (weights of w->second_q, A view of the centre tap)
 };
 
 void make_schedule(const dlq_conv_weights* w, std::vector<SubDesc>& subs, std::vector<StepDesc>& steps) {
@@ -67,6 +68,8 @@ void make_schedule(const dlq_conv_weights* w, std::vector<SubDesc>& subs, std::v
           const int s = static_cast<int>(subs.size());
           subs.push_back({kb * rowb, pl.col0, pl.row_off_rel});
           for (const Tap& t : pl.taps) steps.push_back({s, t.kh, t.kw, kb, t.da, t.db});
+          // fused 1x1/s2 shortcut: input (2 oh, 2 ow) is the (even, even) plane at shift 0 - the centre tap's view
+          if (w->fused && pl.row_off_rel == 0 && pl.col0 == 0) steps.push_back({s, 0, 0, kb, 0, 0, 1});
         }
       break;
     }
@@ -113,7 +116,7 @@ int conv_required_in_pr(const dlq_conv_weights* w) {
 }
 
 int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
-                      int pW, dlq_conv_weights* out) {
+                      int pW, dlq_conv_weights* out, const int8_t* second_wq) {
   DLQ_ARG(ctx, OC > 0 && OC % 64 == 0, "OC must be a multiple of 64");
   DLQ_ARG(ctx, kH == kW && sH == sW && pH == pW, "square kernels / strides / pads only");
   out->OC = OC; out->IC = IC; out->kH = kH; out->kW = kW; out->sH = sH; out->sW = sW; out->pH = pH; out->pW = pW;
@@ -139,6 +142,12 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
   // 64 tensor cycles, inside the 128 B/clk shared-memory budget; 64-channel layers stay single-CTA
   out->n_tile = (OC % 128 == 0) ? 128 : 64;
   if (const char* e = getenv("DLQ_DBG_NTILE")) { const int v = atoi(e); if (v >= 64 && OC % v == 0) out->n_tile = v; }
+  out->fused = 0;
+  if (second_wq) {
+    DLQ_ARG(ctx, out->kind == CONV_S2_3x3, "a fused 1x1/s2 shortcut needs a 3x3/s2/p1 main conv");
+    out->fused = 1;
+    out->second_q.assign(second_wq, second_wq + static_cast<size_t>(OC) * IC);
+  }
   std::vector<SubDesc> subs;
   std::vector<StepDesc> steps;
   make_schedule(out, subs, steps);
@@ -168,6 +177,9 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
               if (c < 3 && kh >= 0 && kh < 7 && kw >= 0 && kw < 7) v = W(o, c, kh, kw);
               dst[swz_off(n, j * 16 + t, 32)] = static_cast<uint8_t>(v);
             }
+        } else if (sd.second) {
+          for (int k = 0; k < out->rowb; ++k)      // shortcut weights: OC x IC (1x1)
+            dst[swz_off(n, k, out->rowb)] = static_cast<uint8_t>(out->second_q[static_cast<size_t>(o) * IC + sd.kb * out->rowb + k]);
         } else {
           for (int k = 0; k < out->rowb; ++k)
             dst[swz_off(n, k, out->rowb)] = static_cast<uint8_t>(W(o, sd.kb * out->rowb + k, sd.kh, sd.kw));
@@ -181,7 +193,8 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
 }
 
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
-              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L) {
+              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L,
+              const SecondConv* second) {
   ConvKernelParams& p = L->p;
   memset(&p, 0, sizeof(p));
   L->fp8 = w->fp8;
@@ -232,9 +245,12 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.n_sub = static_cast<int>(subs.size());
   p.n_steps = static_cast<int>(steps.size());
   int maxshift = 0;
+  p.fused = w->fused;
+  p.first_second_step = -1;
   for (int k = 0; k < p.n_steps; ++k) {
     const int sh = steps[k].da * p.Wp + steps[k].db;
-    p.step_a16[k] = static_cast<uint16_t>(sh * rowb / 16);
+    p.step_a16[k] = static_cast<uint16_t>(sh * rowb / 16) | (steps[k].second ? kStepSecond : 0);
+    if (steps[k].second && p.first_second_step < 0) p.first_second_step = k;
     maxshift = std::max(maxshift, sh);
   }
   for (int s = 0; s < p.n_sub; ++s) {
@@ -261,9 +277,10 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.w_rows = w->n_tile / ncta;
   p.step_bytes = static_cast<uint32_t>(p.w_rows) * rowb;
   const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 1024 /*barriers, step table*/ -
-                        8 * static_cast<size_t>(w->OC) /*alpha, beta*/ - 16 * kEpiStageBytes;
+                        16 * static_cast<size_t>(w->OC) /*alpha, beta (x2 when fused)*/ - 16 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
+  if (w->fused) MT = 1;      // two accumulator blocks per tile: 2 * n_tile columns per stage
   if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * p.n_tile <= 512) MT = v; }
   int NR = 0;
   const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;
@@ -293,7 +310,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   DLQ_ARG(ctx, p.a_stages >= 1 && p.b_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256 && w->OC <= 2048,
           "conv patch does not fit shared memory / TMA box");
   p.MT = MT;
-  p.acc_stages = (2 * MT * p.n_tile <= 512) ? 2 : 1;
+  p.acc_stages = (2 * MT * p.n_tile * (w->fused ? 2 : 1) <= 512) ? 2 : 1;
   p.super_stride = p.two ? ((MT * kTileM) / p.Wp) * p.Wp : MT * kTileM;
   const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
   DLQ_ARG(ctx, total_pos + 4LL * MT * kTileM < (1LL << 31), "batch too large for 32-bit position arithmetic");
@@ -318,6 +335,14 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.out = out.ptr;
   p.out_PR = out.PR;
   p.acc_out = acc_out;
+  if (w->fused) {
+    DLQ_ARG(ctx, second && second->out.ptr && second->alpha && second->beta && !residual && !acc_out && MT == 1,
+            "fused shortcut conv: needs its own output / alpha / beta, no residual, one tile per item");
+    DLQ_ARG(ctx, second->out.N == in.N && second->out.H == p.Ho && second->out.W == p.Wo && second->out.C == w->OC,
+            "fused shortcut conv: output geometry mismatch");
+    p.alpha2 = second->alpha; p.beta2 = second->beta; p.relu2 = second->relu;
+    p.out2 = second->out.ptr; p.out2_PR = second->out.PR;
+  }
   if (getenv("DLQ_DBG_NO_STORE")) { p.out = nullptr; p.acc_out = nullptr; }
   if (const char* e = getenv("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
   // DLQ_DBG_TIMES=1: per-CTA cycle counters (MMA warp: total / wait acc_empty / wait a_full / wait b_full;
@@ -372,7 +397,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   L->grid = dim3(static_cast<unsigned>(G * ncta), 1, 1);
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
-            2 * sizeof(float) * w->OC + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) +
+            4 * sizeof(float) * w->OC + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) +
             8 * (2 * p.a_stages + 2 * p.b_stages + 3 * p.acc_stages) + 16;
   return DLQ_OK;
 }

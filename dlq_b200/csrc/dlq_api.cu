@@ -413,6 +413,7 @@ struct dlq_resnet18 {
   float* d_beta[DLQ_NUM_CONVS] = {nullptr};
   float act_scale[DLQ_NUM_ACTS];
   int fp8 = 0;                // E4M3 activations / weights, FP32 accumulation (else int8 / int32)
+  bool fuse_ds = true;        // downsample blocks: the 1x1/s2 shortcut conv rides on conv1's launch (one patch load)
   int8_t* d_fc_w = nullptr;
   float* d_fc_scale = nullptr;
   float* d_fc_bias = nullptr;
@@ -421,11 +422,13 @@ struct dlq_resnet18 {
   Act a_in, a_stem, a_pool;
   Act a_t1[8], a_ds[8], a_out[8];
   std::vector<void*> allocs;
+  dlq_conv_weights* conv_fused[8] = {nullptr};   // downsample blocks: conv1 + shortcut in one weight image (small batches)
   float* d_x = nullptr;       // staging for forward_host
   float* d_logits = nullptr;
   struct Plan {
     int N = 0;
     ConvLaunch L[DLQ_NUM_CONVS];
+    bool fused[8] = {false};    // block b's shortcut conv runs inside L[conv1 of b]
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
@@ -475,6 +478,7 @@ inline int act_c1(int b) { return 2 + 3 * b; }
 inline int act_ds(int b) { return 3 + 3 * b; }
 inline int act_out(int b) { return 4 + 3 * b; }
 constexpr int kActInput = 0, kActStem = 1, kActGap = 26;
+constexpr int kFuseMaxBatch = 16;
 
 int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   dlq_ctx* ctx = m->ctx;
@@ -488,12 +492,23 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   for (int b = 0; b < 8; ++b) {
     const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, id = 3 + 3 * b;
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
-    rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1]);
+    // Fusing the shortcut into conv1 saves a launch and a second pass over the input, but forces one tile per
+    // item (two accumulator blocks per tile in TMEM): it wins at small batches (latency), loses at large ones.
+    P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= kFuseMaxBatch;
+    if (P->fused[b]) {
+      SecondConv sc;
+      sc.alpha = m->d_alpha[id]; sc.beta = m->d_beta[id]; sc.relu = 0; sc.out = with_n(m->a_ds[b], N);
+      rc = plan_conv(ctx, m->conv_fused[b], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1], &sc);
+    } else {
+      rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1]);
+    }
     if (rc != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       Act ds = with_n(m->a_ds[b], N);
-      rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, nullptr, &P->L[id]);
-      if (rc != DLQ_OK) return rc;
+      if (!P->fused[b]) {
+        rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, nullptr, &P->L[id]);
+        if (rc != DLQ_OK) return rc;
+      }
       rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &ds, dlq_res_mul(S[act_ds(b)], S[act_out(b)]), 1,
                      nullptr, &P->L[i2]);
     } else {
@@ -515,6 +530,7 @@ void dlq_resnet18_destroy(dlq_resnet18* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   cudaStreamSynchronize(m->ctx->stream);
+  for (auto*& cw : m->conv_fused) { if (cw) { dlq_conv_weights_free(cw); cw = nullptr; } }
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->graph) cudaGraphDestroy(m->graph);
   for (void* p : m->allocs) cudaFree(p);
@@ -541,6 +557,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   m->max_batch = max_batch;
   std::copy(w->act_scale, w->act_scale + DLQ_NUM_ACTS, m->act_scale);
   m->fp8 = w->fp8 ? 1 : 0;
+  m->fuse_ds = getenv("DLQ_NO_FUSE_DS") == nullptr;
 
   // ---- convs: geometry as wired by runtime/infer_e2e.cu:258-407
   struct CG { int ic, oc, k, s, p; float s_in, s_out; };
@@ -565,6 +582,22 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     int rc = m->fp8 ? dlq_conv_weights_pack_fp8(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i])
                     : dlq_conv_weights_pack(ctx, w->conv_w[i], g.oc, g.ic, g.k, g.k, g.s, g.s, g.p, g.p, s_w.data(), &m->conv[i]);
     if (rc != DLQ_OK) return rc;
+    const bool is_c1_of_down = m->fuse_ds && i >= 1 && (i - 1) % 3 == 0 && kBlocks[(i - 1) / 3].down;
+    if (is_c1_of_down) {
+      // small batches additionally get ONE launch for conv1 + the 1x1/s2 shortcut: both weight sets in one image
+      // (conv1's K steps + the shortcut's, which reads the centre tap's view of the same patch)
+      std::vector<int8_t> q1, q2;
+      std::vector<float> s1, s2;
+      const CG& gd = geo[i + 2];
+      if (m->fp8) { quantize_rows_e4m3(w->conv_w[i], g.oc, g.ic * 9, q1, s1); quantize_rows_e4m3(w->conv_w[i + 2], gd.oc, gd.ic, q2, s2); }
+      else { quantize_rows(w->conv_w[i], g.oc, g.ic * 9, q1, s1); quantize_rows(w->conv_w[i + 2], gd.oc, gd.ic, q2, s2); }
+      std::unique_ptr<dlq_conv_weights> cw(new dlq_conv_weights());
+      rc = pack_conv_weights(ctx, q1.data(), g.oc, g.ic, 3, 3, 2, 2, 1, 1, cw.get(), q2.data());
+      if (rc != DLQ_OK) { if (cw->d_img) cudaFree(cw->d_img); return rc; }
+      cw->fp8 = m->fp8;
+      cw->scale = s1;
+      m->conv_fused[(i - 1) / 3] = cw.release();
+    }
     // folded constants, QUANT_SPEC §3 (double arithmetic, rounded once)
     std::vector<float> alpha(g.oc), beta(g.oc);
     dlq_fold_bn(w->bn_gamma[i], w->bn_beta[i], w->bn_mean[i], w->bn_var[i], 1e-5f, s_w.data(), g.s_in, g.s_out, g.oc,
@@ -670,8 +703,10 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
     if (rc != DLQ_OK) return rc;
     if ((rc = mark()) != DLQ_OK) return rc;
     if (kBlocks[b].down) {
-      rc = launch_conv(ctx, P.L[3 + 3 * b]);
-      if (rc != DLQ_OK) return rc;
+      if (!P.fused[b]) {          // (fused: the shortcut conv ran inside conv1's launch; its profile entry stays 0)
+        rc = launch_conv(ctx, P.L[3 + 3 * b]);
+        if (rc != DLQ_OK) return rc;
+      }
       if ((rc = mark()) != DLQ_OK) return rc;
     }
     rc = launch_conv(ctx, P.L[2 + 3 * b]);

@@ -68,6 +68,8 @@ struct dlq_conv_weights {
   uint32_t step_bytes = 0;
   uint8_t* d_img = nullptr;   // device: [OC/n_tile][n_steps][step_bytes]
   int fp8 = 0;                // 1: the bytes are E4M3 (QUANT_SPEC section 6), else signed int8
+  int fused = 0;              // 1: a 1x1/s2 shortcut conv (second_q, OC x IC) rides on this 3x3/s2 conv's patch loads
+  std::vector<int8_t> second_q;
   std::vector<int8_t> q_oihw; // host copy of the quantised weights (tests / checkpoints)
   std::vector<float> scale;   // per-output-channel scale
   int device = 0;
@@ -77,7 +79,14 @@ namespace dlq {
 
 // conv_plan.cu
 int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, int kW, int sH, int sW, int pH,
-                      int pW, dlq_conv_weights* out);
+                      int pW, dlq_conv_weights* out, const int8_t* second_wq = nullptr);
+// epilogue of the fused shortcut conv (its own folded constants, ReLU flag and output tensor)
+struct SecondConv {
+  const float* alpha = nullptr;
+  const float* beta = nullptr;
+  int relu = 0;
+  Act out;
+};
 // PR the conv requires of its input tensor (and whether the image pitch must be even)
 int conv_required_in_pr(const dlq_conv_weights* w);
 struct ConvLaunch {
@@ -91,7 +100,8 @@ struct ConvLaunch {
 };
 // Build the launch for conv `w` reading `in` and writing `out` (either of out.ptr / acc_out may be null).
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
-              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L);
+              const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L,
+              const SecondConv* second = nullptr);
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L);
 void conv_out_dims(const dlq_conv_weights* w, int H, int W, int* OH, int* OW);
 
