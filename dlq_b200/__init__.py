@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "dlq_bn_inference_f32", "dlq_relu_forward_f32", "dlq_relu_forward_i8", "dlq_add_inplace_f32", "dlq_add_requant_i8",
     "dlq_maxpool2d_3x3_s2p1_nchw_i8", "dlq_gap_global_i8", "dlq_fc_forward_i8", "dlq_softmax_f32",
     "dlq_resnet18_create", "dlq_resnet18_destroy", "dlq_resnet18_forward", "dlq_resnet18_forward_host",
+    "dlq_resnet18_set_preprocess", "dlq_resnet18_forward_u8", "dlq_resnet18_forward_host_u8",
     "dlq_resnet18_checkpoint", "dlq_resnet18_graph_capture", "dlq_resnet18_graph_launch", "dlq_resnet18_launches", "dlq_resnet18_profile", "dlq_synth_fill_f32",
     "dlq_multi_create", "dlq_multi_destroy", "dlq_multi_forward_host", "dlq_multi_last_error_string",
 ]
@@ -128,6 +129,9 @@ def load_library() -> C.CDLL:
         "dlq_resnet18_forward_host": (i, [vp, vp, i, vp]),
         "dlq_resnet18_checkpoint": (i, [vp, C.c_char_p, vp]),
         "dlq_resnet18_graph_capture": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_set_preprocess": (i, [vp, vp, vp]),
+        "dlq_resnet18_forward_u8": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_forward_host_u8": (i, [vp, vp, i, vp]),
         "dlq_resnet18_graph_launch": (i, [vp]),
         "dlq_resnet18_launches": (i, [vp]),
         "dlq_resnet18_profile": (i, [vp, vp, i, vp, vp]),
@@ -423,6 +427,23 @@ class ResNet18:
         xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
         lp = logits_host.data_ptr() if hasattr(logits_host, "data_ptr") else logits_host.ctypes.data
         self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_host(self.h, xp, x_host.shape[0], lp))
+
+    IMAGENET_MEAN = (0.485, 0.456, 0.406)     # the reference's tools/preprocess_to_bin.py:5-6
+    IMAGENET_STD = (0.229, 0.224, 0.225)
+
+    def set_preprocess(self, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+        mean = np.asarray(mean, dtype=np.float32)
+        std = np.asarray(std, dtype=np.float32)
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_set_preprocess(self.h, mean.ctypes.data, std.ctypes.data))
+
+    def forward_u8(self, x_hwc, logits):
+        """x_hwc: uint8 [N,224,224,3] device tensor (RGB); needs set_preprocess() first"""
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_u8(self.h, _ptr(x_hwc), x_hwc.shape[0], _ptr(logits)))
+
+    def forward_host_u8(self, x_hwc_host, logits_host):
+        xp = x_hwc_host.data_ptr() if hasattr(x_hwc_host, "data_ptr") else x_hwc_host.ctypes.data
+        lp = logits_host.data_ptr() if hasattr(logits_host, "data_ptr") else logits_host.ctypes.data
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_host_u8(self.h, xp, x_hwc_host.shape[0], lp))
 
     def checkpoint(self, name: str, out):
         self.ctx._ck(self.ctx.lib.dlq_resnet18_checkpoint(self.h, name.encode(), _ptr(out)))

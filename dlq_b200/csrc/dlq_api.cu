@@ -413,6 +413,7 @@ struct dlq_resnet18 {
   float* d_beta[DLQ_NUM_CONVS] = {nullptr};
   float act_scale[DLQ_NUM_ACTS];
   int fp8 = 0;                // E4M3 activations / weights, FP32 accumulation (else int8 / int32)
+  bool has_lut = false;       // dlq_resnet18_set_preprocess was called
   bool fuse_ds = true;        // downsample blocks: the 1x1/s2 shortcut conv rides on conv1's launch (one patch load)
   int8_t* d_fc_w = nullptr;
   float* d_fc_scale = nullptr;
@@ -423,6 +424,8 @@ struct dlq_resnet18 {
   Act a_t1[8], a_ds[8], a_out[8];
   std::vector<void*> allocs;
   dlq_conv_weights* conv_fused[8] = {nullptr};   // downsample blocks: conv1 + shortcut in one weight image (small batches)
+  uint8_t* d_lut = nullptr;   // [3][256] uint8 pixel value -> quantised stem input (dlq_resnet18_set_preprocess)
+  uint8_t* d_xu8 = nullptr;   // staging for forward_host_u8
   float* d_x = nullptr;       // staging for forward_host
   float* d_logits = nullptr;
   struct Plan {
@@ -652,6 +655,12 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 1000 * sizeof(float)));
     m->allocs.push_back(p);
     m->d_logits = static_cast<float*>(p);
+    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 3 * 224 * 224));
+    m->allocs.push_back(p);
+    m->d_xu8 = static_cast<uint8_t*>(p);
+    DLQ_CUDA(ctx, cudaMalloc(&p, 768));
+    m->allocs.push_back(p);
+    m->d_lut = static_cast<uint8_t*>(p);
   }
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   // plan the full batch now so the first forward does no host planning
@@ -668,9 +677,11 @@ int dlq_resnet18_launches(const dlq_resnet18* m) {
   return 1 /*quantise+s2d*/ + 20 /*convs*/ + 1 /*max-pool*/ + 1 /*GAP+FC*/;
 }
 
-static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, cudaEvent_t* ev) {
+// x: fp32 NCHW input, or (x == nullptr) x_u8: uint8 HWC images mapped through m->d_lut
+static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, cudaEvent_t* ev,
+                        const uint8_t* x_u8 = nullptr) {
   dlq_ctx* ctx = m->ctx;
-  DLQ_ARG(ctx, x && logits && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  DLQ_ARG(ctx, (x || x_u8) && logits && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
   if (N == 0) return DLQ_OK;
   DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
   auto it = m->plans.find(N);
@@ -689,7 +700,8 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   };
   int rc = mark();
   if (rc != DLQ_OK) return rc;
-  rc = quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N), m->fp8);
+  rc = x ? quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N), m->fp8)
+         : preprocess_u8_s2d(ctx, x_u8, N, 224, 224, m->d_lut, with_n(m->a_in, N));
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   rc = launch_conv(ctx, P.L[0]);
@@ -813,6 +825,77 @@ int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float
                                 cudaMemcpyDeviceToHost, ctx->stream));
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   m->last_N = std::min(chunk, N - (k - 1) * chunk);   // checkpoints refer to the last chunk
+  return DLQ_OK;
+}
+
+/* uint8 input path.  The reference normalises on the host in Python (tools/preprocess_to_bin.py:24-33:
+ * x = u8 / 255, (x - mean) / std in float32) and feeds fp32; here the normalisation and the input quantisation are a
+ * 3 x 256 byte table applied on the device, built with exactly that fp32 arithmetic, so the logits are bit-identical
+ * to dlq_resnet18_forward on the fp32 tensor the reference's preprocessing would have produced. */
+int dlq_resnet18_set_preprocess(dlq_resnet18* m, const float* mean3, const float* std3) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, mean3 && std3 && std3[0] > 0.f && std3[1] > 0.f && std3[2] > 0.f, "null pointer or non-positive std");
+  std::vector<uint8_t> lut(768);
+  const float inv = inv_scale(m->act_scale[kActInput]);
+  for (int c = 0; c < 3; ++c)
+    for (int u = 0; u < 256; ++u) {
+      volatile float v = static_cast<float>(u) / 255.0f;      // (volatile: every step rounded to binary32, as numpy does)
+      v = v - mean3[c];
+      v = v / std3[c];
+      v = v * inv;
+      lut[c * 256 + u] = m->fp8 ? f32_to_e4m3_host(v) : static_cast<uint8_t>(quant_host(v, -128, 127));
+    }
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_lut, lut.data(), 768, cudaMemcpyHostToDevice, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->has_lut = true;
+  return DLQ_OK;
+}
+
+/* x_hwc: uint8 [N,224,224,3] device; logits: fp32 [N,1000] device */
+int dlq_resnet18_forward_u8(dlq_resnet18* m, const uint8_t* x_hwc, int N, float* logits) {
+  if (!m) return DLQ_ERR_ARG;
+  DLQ_ARG(m->ctx, m->has_lut, "call dlq_resnet18_set_preprocess first");
+  return forward_impl(m, nullptr, N, logits, nullptr, x_hwc);
+}
+
+/* same with HOST buffers: H2D of the uint8 images (150 KB/image instead of 602 KB), forward, D2H of the logits;
+ * large batches are pipelined in chunks like dlq_resnet18_forward_host */
+int dlq_resnet18_forward_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int N, float* logits_host) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, x_hwc_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  DLQ_ARG(ctx, m->has_lut, "call dlq_resnet18_set_preprocess first");
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t img = static_cast<size_t>(3) * 224 * 224;
+  const int chunk = (N >= 256) ? 128 : (N >= 128) ? 64 : N;   // (a uint8 chunk copies 4x faster than an fp32 one)
+  if (!m->copy_stream) {
+    DLQ_CUDA(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : m->copy_done) DLQ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    DLQ_CUDA(ctx, cudaEventCreateWithFlags(&m->compute_done, cudaEventDisableTiming));
+  }
+  DLQ_CUDA(ctx, cudaEventRecord(m->compute_done, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->compute_done, 0));
+  int k = 0;
+  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
+    const int n = std::min(chunk, N - n0);
+    DLQ_ARG(ctx, k < static_cast<int>(sizeof(m->copy_done) / sizeof(m->copy_done[0])), "too many chunks");
+    DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_xu8 + n0 * img, x_hwc_host + n0 * img, n * img, cudaMemcpyHostToDevice, m->copy_stream));
+    DLQ_CUDA(ctx, cudaEventRecord(m->copy_done[k], m->copy_stream));
+  }
+  k = 0;
+  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
+    const int n = std::min(chunk, N - n0);
+    DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copy_done[k], 0));
+    const int rc = forward_impl(m, nullptr, n, m->d_logits + static_cast<size_t>(n0) * 1000, nullptr, m->d_xu8 + n0 * img);
+    if (rc != DLQ_OK) return rc;
+  }
+  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, m->d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->last_N = std::min(chunk, N - (k - 1) * chunk);
   return DLQ_OK;
 }
 

@@ -111,6 +111,7 @@ int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y);                // row
 int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32_t* y);
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a);   // C=3 int8 NCHW -> s2d
 int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a, int fp8 = 0);
+int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a);
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out);
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
                const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);

@@ -186,6 +186,13 @@ void dlq_resnet18_destroy(dlq_resnet18* m);
 int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits);
 /* same with HOST buffers (pinned or pageable): H2D copy, forward, D2H copy, synchronise */
 int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host);
+/* uint8 image input (the adjacent stage of the reference's pipeline, tools/preprocess_to_bin.py:24-33: u8/255,
+ * (x-mean)/std in float32, HWC -> CHW): normalisation + input quantisation become a 3x256 byte table applied on the
+ * device, built with that fp32 arithmetic, so logits equal dlq_resnet18_forward on the tensor the reference's
+ * preprocessing produces.  x_hwc: uint8 [N,224,224,3] (RGB).  Host variant: 150 KB/image of H2D instead of 602 KB. */
+int dlq_resnet18_set_preprocess(dlq_resnet18* m, const float* mean3, const float* std3);
+int dlq_resnet18_forward_u8(dlq_resnet18* m, const uint8_t* x_hwc, int N, float* logits);
+int dlq_resnet18_forward_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int N, float* logits_host);
 /* int8 NCHW copy of an internal checkpoint of the LAST forward: "stem_pool","layer1".."layer4","gap"
  * (names as R/infer_e2e.cu:297-426 dumps them).  out is a device pointer. */
 int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);

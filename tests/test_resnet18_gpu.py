@@ -92,3 +92,34 @@ def test_forward_host_and_quantised_accuracy(ctx, model256):
     for i in range(2):
         cos = float(np.dot(f[i], lh.numpy()[i]) / (np.linalg.norm(f[i]) * np.linalg.norm(lh.numpy()[i])))
         assert cos > 0.98, cos
+
+
+@pytest.mark.gpu
+def test_u8_input_path_equals_reference_preprocessing():
+    """uint8 HWC images through the device-side table == the reference's numpy preprocessing
+    (tools/preprocess_to_bin.py:24-33) followed by the fp32 entry point, bit for bit; host-buffer variant too."""
+    import torch
+    import dlq_b200
+    from dlq_b200 import synth
+    rng = np.random.default_rng(7)
+    n = 5
+    u8 = rng.integers(0, 256, (n, 224, 224, 3), dtype=np.uint8)
+    mean = np.array(dlq_b200.ResNet18.IMAGENET_MEAN, dtype=np.float32)
+    std = np.array(dlq_b200.ResNet18.IMAGENET_STD, dtype=np.float32)
+    x = u8.astype(np.float32) / 255.0
+    x = (x - mean) / std
+    x = np.ascontiguousarray(np.transpose(x, (0, 3, 1, 2)))
+    ctx = dlq_b200.Context(0)
+    m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    m.set_preprocess()
+    ref = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    got = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    m.forward(torch.from_numpy(x).cuda(), ref)
+    m.forward_u8(torch.from_numpy(u8).cuda(), got)
+    ctx.sync()
+    assert torch.equal(ref, got)
+    host = np.empty((n, 1000), dtype=np.float32)
+    m.forward_host_u8(u8, host)
+    assert np.array_equal(host.view(np.uint32), ref.cpu().numpy().view(np.uint32))
+    m.close()
+    ctx.close()

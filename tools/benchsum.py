@@ -5,3 +5,4 @@ print("img/s %.0f  ms/step %.4f  conv_ms %.4f  frac %.3f  e2e %.0f  clocks %s" %
 pl = r["per_launch_ms"]
 print(" ".join(f"{k.replace('layer','L').replace('downsample','ds').replace('conv','c')}={v*1000:.0f}" for k, v in pl.items()))
 print("fp8:", d.get("fp8"), "| latency_b1:", d.get("latency_b1"))
+print("e2e_u8:", (d.get("e2e_u8") or {}).get("value"))
