@@ -317,6 +317,14 @@ __device__ __forceinline__ void epi_prefetch_res(const ConvKernelParams& p, cons
   }
 }
 
+// byte K of w (value + 128, i.e. already XORed with 0x80) -> float(value), exact: 0x4B0000uu is 2^23 + uu
+template <int K>
+__device__ __forceinline__ float biased_byte_to_float(uint32_t w) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(0x4B000000u), "r"(0x7650u + K));
+  return __int_as_float(static_cast<int>(r)) - 8388736.0f;
+}
+
 // two independent round-to-nearest fp32 FMAs in one instruction (sm_100 FFMA2); bit-identical to two fmaf
 __device__ __forceinline__ void fma2_rn(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
   asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
@@ -417,10 +425,11 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
             fma2_rn(t0, t1, r01.x, r01.y, e.res_mul, e.res_mul, t0, t1);
             fma2_rn(t2, t3, r23.x, r23.y, e.res_mul, e.res_mul, t2, t3);
           } else {
-            fma2_rn(t0, t1, static_cast<float>(static_cast<int8_t>(w)), static_cast<float>(static_cast<int8_t>(w >> 8)),
-                    e.res_mul, e.res_mul, t0, t1);
-            fma2_rn(t2, t3, static_cast<float>(static_cast<int8_t>(w >> 16)), static_cast<float>(static_cast<int8_t>(w >> 24)),
-                    e.res_mul, e.res_mul, t2, t3);
+            // int8 -> float without the conversion pipe: byte + 128 dropped into the mantissa of 2^23 (PRMT), then
+            // an exact subtraction of 2^23 + 128
+            const uint32_t wb = w ^ 0x80808080u;
+            fma2_rn(t0, t1, biased_byte_to_float<0>(wb), biased_byte_to_float<1>(wb), e.res_mul, e.res_mul, t0, t1);
+            fma2_rn(t2, t3, biased_byte_to_float<2>(wb), biased_byte_to_float<3>(wb), e.res_mul, e.res_mul, t2, t3);
           }
         }
         const uint32_t q = FP8 ? pack_e4m3x4(t0, t1, t2, t3)
