@@ -74,6 +74,7 @@ struct ConvKernelParams {
   int16_t sub_c0[16];     // TMA coordinates per sub-patch: channel byte offset
   int16_t sub_col0[16];   //   start column (may be negative)
   int16_t sub_row_off[16];//   row offset
+  int sub_plane_row[16];  //   + first row of the sub-patch's parity plane (plane-layout inputs, else 0)
   int16_t sub_step0[17];  //   first K step of each sub-patch (sub_step0[n_sub] = n_steps)
   // K steps
   int n_steps;
@@ -92,6 +93,8 @@ struct ConvKernelParams {
   int relu;               // lo = relu ? 0 : -128
   int8_t* out;            // row-padded NHWC int8
   int out_PR;
+  int out_planes;         // 1: out is stored as four parity planes (see Act::planes); out_rows_half = total rows / 2
+  int out_rows_half;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
   // Fused second conv (ResNet downsample blocks, R/infer_e2e.cu:181-196): the 1x1/s2 shortcut conv reads exactly the
   // A view of the 3x3/s2 conv's centre tap, so both run from ONE patch load: steps flagged kStepSecond multiply that
@@ -357,7 +360,13 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   for (int u = 0; u < NU; ++u) {
     int n, r, x;
     valid[u] = decode_pos(p, g_own[u], n, r, x);
-    opix[u] = valid[u] ? static_cast<uint32_t>((e.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
+    if (p.out_planes) {       // (never combined with the fused second conv)
+      const int prow = e.out_PR + n * e.out_pitch + r;
+      const int pl = ((prow & 1) << 1) | (x & 1);
+      opix[u] = valid[u] ? static_cast<uint32_t>((pl * p.out_rows_half + (prow >> 1)) * (p.Wo >> 1) + (x >> 1)) : kInvalidPix;
+    } else {
+      opix[u] = valid[u] ? static_cast<uint32_t>((e.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
+    }
     dpix[u] = ACC_OUT ? (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x : 0;
   }
   uint8_t* my_row[NU];    // own staged row (row = lane); chunk q sits at my_row + ((q ^ my_swz) << 4)
@@ -576,10 +585,11 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
             // transaction bytes on the rank-0 barrier (a remote arrive per load would cost a cluster round trip)
             if (rank == 0) mbar_expect_tx(&a_full[as], 2u * static_cast<uint32_t>(p.tma_bytes));
             tma_load_3d_pair(dst, &tm0, leader_cta_addr(&a_full[as]), p.sub_c0[s], p.sub_col0[s],
-                             p.row_mul * v0 + p.sub_row_off[s]);
+                             p.row_mul * v0 + p.sub_row_off[s] + p.sub_plane_row[s]);
           } else {
             mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
-            tma_load_3d(dst, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s], p.row_mul * v0 + p.sub_row_off[s]);
+            tma_load_3d(dst, &tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
+                        p.row_mul * v0 + p.sub_row_off[s] + p.sub_plane_row[s]);
           }
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }

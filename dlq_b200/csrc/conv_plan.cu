@@ -253,11 +253,27 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     if (steps[k].second && p.first_second_step < 0) p.first_second_step = k;
     maxshift = std::max(maxshift, sh);
   }
+  const bool in_planes = in.planes && es == 2;
+  DLQ_ARG(ctx, !in.planes || (es == 2 && in.rows() % 2 == 0 && in.W % 2 == 0), "plane layout is for stride-2 convs over even tensors");
+  const int rows_half = in.planes ? in.plane_rows : in.rows() / 2;
+  DLQ_ARG(ctx, !in.planes || in.plane_rows >= in.rows() / 2, "plane layout: plane_rows smaller than the tensor");
   for (int s = 0; s < p.n_sub; ++s) {
     p.sub_c0[s] = static_cast<int16_t>(subs[s].c0);
-    p.sub_col0[s] = static_cast<int16_t>(subs[s].col0);
-    p.sub_row_off[s] = static_cast<int16_t>(in.PR + subs[s].row_off_rel);
+    if (in_planes) {
+      // parity plane (pr, pc) of the physical start (row 2 v0 + PR + rel, col col0): dense box inside that plane
+      const int srow = in.PR + subs[s].row_off_rel, scol = subs[s].col0;
+      const int pr = srow & 1, pc = scol & 1;
+      p.sub_col0[s] = static_cast<int16_t>((scol - pc) / 2);
+      DLQ_ARG(ctx, (pr * 2 + pc) * rows_half + (srow >> 1) < 32768, "tensor too tall for 16-bit plane row offsets");
+      p.sub_row_off[s] = static_cast<int16_t>(srow >> 1);
+      p.sub_plane_row[s] = (pr * 2 + pc) * rows_half;
+    } else {
+      p.sub_col0[s] = static_cast<int16_t>(subs[s].col0);
+      p.sub_row_off[s] = static_cast<int16_t>(in.PR + subs[s].row_off_rel);
+      p.sub_plane_row[s] = 0;
+    }
   }
+  if (in_planes) p.row_mul = 1;
   {
     int k = 0;
     for (int s = 0; s < p.n_sub; ++s) {
@@ -334,6 +350,9 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   p.relu = relu;
   p.out = out.ptr;
   p.out_PR = out.PR;
+  p.out_planes = out.planes;
+  p.out_rows_half = out.planes ? out.plane_rows : out.rows() / 2;
+  DLQ_ARG(ctx, !out.planes || (out.rows() % 2 == 0 && out.W % 2 == 0 && !w->fused), "plane-layout output needs even rows / width");
   p.acc_out = acc_out;
   if (w->fused) {
     DLQ_ARG(ctx, second && second->out.ptr && second->alpha && second->beta && !residual && !acc_out && MT == 1,
@@ -360,12 +379,13 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     ctx->err = "cuTensorMapEncodeTiled entry point not available";
     return DLQ_ERR_CUDA;
   }
-  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in.W),
-                        static_cast<cuuint64_t>(in.rows())};
-  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in.C) * in.W};
-  cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb), static_cast<cuuint32_t>(es * p.Wp),
-                       static_cast<cuuint32_t>(es * NR)};
-  cuuint32_t estr[3] = {1, static_cast<cuuint32_t>(es), static_cast<cuuint32_t>(es)};
+  const int tes = in_planes ? 1 : es;       // plane layout: dense boxes inside a [C][W/2][4 * rows/2] tensor
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in_planes ? in.W / 2 : in.W),
+                        static_cast<cuuint64_t>(in_planes ? 4 * rows_half : in.rows())};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(in.C), static_cast<cuuint64_t>(in.C) * (in_planes ? in.W / 2 : in.W)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(rowb), static_cast<cuuint32_t>(tes * p.Wp),
+                       static_cast<cuuint32_t>(tes * NR)};
+  cuuint32_t estr[3] = {1, static_cast<cuuint32_t>(tes), static_cast<cuuint32_t>(tes)};
   const CUtensorMapSwizzle swz = rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                               : CU_TENSOR_MAP_SWIZZLE_32B;

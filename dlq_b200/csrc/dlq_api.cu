@@ -642,6 +642,11 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     rc = alloc_act(m.get(), m->a_t1[b], N, hw, hw, B.oc, 1);
     if (rc == DLQ_OK && B.down) rc = alloc_act(m.get(), m->a_ds[b], N, hw, hw, B.oc, 0);
     if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_out[b], N, hw, hw, B.oc, feeds_s2 ? 2 : 1);
+    // a block output that only the next block's stride-2 convs read is kept as four parity planes
+    if (rc == DLQ_OK && feeds_s2 && !getenv("DLQ_NO_PLANES")) {
+      m->a_out[b].planes = 1;
+      m->a_out[b].plane_rows = m->a_out[b].rows() / 2;
+    }
   }
   if (rc != DLQ_OK) return rc;
   {

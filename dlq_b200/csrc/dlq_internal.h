@@ -47,6 +47,12 @@ namespace dlq {
 struct Act {
   int8_t* ptr = nullptr;
   int N = 0, H = 0, W = 0, C = 0, PR = 0;
+  // planes = 1: the same rows x W pixels stored as four parity planes [row&1][col&1][rows/2][W/2][C] (rows and W
+  // even).  Tensors read only by stride-2 convs use it: each parity plane is then a dense TMA box instead of an
+  // elementStrides = 2 gather (which moves 4x the bytes through the TMA unit and writes shared memory pixel-wise).
+  int planes = 0;
+  int plane_rows = 0;   // rows per plane = (rows of the ALLOCATED tensor) / 2: fixed at allocation so that the planes,
+                        // and with them the zero pad rows, do not move when a smaller batch uses the same buffer
   int rows() const { return PR + N * (H + PR); }
   size_t bytes() const { return static_cast<size_t>(rows()) * W * C; }
   size_t row_index(int n, int h) const { return static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR) + h; }

@@ -137,7 +137,7 @@ __global__ void nchw_to_act_kernel(const int8_t* __restrict__ x, int8_t* __restr
 }
 
 __global__ void act_to_nchw_kernel(const int8_t* __restrict__ a, int8_t* __restrict__ y, int N, int C, int H, int W,
-                                   int PR) {
+                                   int PR, int planes, int rows_half) {
   __shared__ int8_t tile[64][64 + 4];
   const int HW = H * W;
   const int ptiles = (HW + 63) / 64, ctiles = C / 64;
@@ -154,7 +154,12 @@ __global__ void act_to_nchw_kernel(const int8_t* __restrict__ a, int8_t* __restr
       if (pix < HW) {
         const int h = pix / W, w = pix % W;
         const size_t row = static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR) + h;
-        v = a[(row * W + w) * C + c0 + c];
+        if (planes) {
+          const size_t pl = ((row & 1) << 1) | (w & 1);
+          v = a[((pl * rows_half + (row >> 1)) * (W >> 1) + (w >> 1)) * C + c0 + c];
+        } else {
+          v = a[(row * W + w) * C + c0 + c];
+        }
       }
       tile[c][pp] = v;
     }
@@ -785,7 +790,7 @@ int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y) {
   DLQ_ARG(ctx, a.C % 64 == 0, "channels must be a multiple of 64");
   const long long tiles = static_cast<long long>(a.N) * ((a.H * a.W + 63) / 64) * (a.C / 64);
   const int grid = static_cast<int>(std::min<long long>(tiles, ctx->num_sms * 16LL));
-  act_to_nchw_kernel<<<std::max(1, grid), 256, 0, ctx->stream>>>(a.ptr, y, a.N, a.C, a.H, a.W, a.PR);
+  act_to_nchw_kernel<<<std::max(1, grid), 256, 0, ctx->stream>>>(a.ptr, y, a.N, a.C, a.H, a.W, a.PR, a.planes, a.plane_rows);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
