@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmw, const ConvKernelParams p) {
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
+  const long long t_entry = clock64();
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B with pointer arithmetic on the __shared__ array (keeps the address space visible to
   // the compiler so alpha/beta reads become LDS, not generic loads)
@@ -561,6 +562,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   if (TWO) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (p.dbg_times && threadIdx.x == 0) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 8] = clock64() - t_entry;   // prologue
 
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
@@ -595,7 +597,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         }
       }
       if (p.dbg_times) {
-        long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
+        long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
         d[6] = clock64() - t_begin; d[7] = t_wait;
       }
     }
@@ -659,8 +661,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0, FP8>(c, tt);
     }
     if (p.dbg_times && c.leader && issuer == 0) {
-      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
+      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
       d[0] = clock64() - t_begin; d[1] = tt[0]; d[2] = tt[1]; d[3] = tt[2];
+      d[9] = clock64() - t_entry;      // issuer done, since kernel entry
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
@@ -777,12 +780,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     }
     if (has_res) cp_async_wait_all();
     if (p.dbg_times && ew == 0 && lane == 0) {
-      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 8;
+      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
       d[4] = clock64() - t_begin; d[5] = t_wait;
     }
   }
+  if (p.dbg_times && threadIdx.x == 128) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 10] = clock64() - t_entry;  // first epilogue warp done
   tc_fence_before();
   __syncthreads();
+  if (p.dbg_times && threadIdx.x == 0) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 11] = clock64() - t_entry;    // CTA done
   if (TWO) cluster_sync_all();   // nobody leaves while the peer may still arrive on its barriers / read its smem
   if (warp == 1) {
     if (TWO) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);

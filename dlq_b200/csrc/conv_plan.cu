@@ -368,8 +368,8 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   // epilogue warp 0: total / wait acc_full; A producer: total / wait a_empty), printed by launch_conv
   if (getenv("DLQ_DBG_TIMES")) {
     static long long* buf = nullptr;
-    if (!buf) cudaMalloc(&buf, 8 * sizeof(long long) * 1024);
-    cudaMemset(buf, 0, 8 * sizeof(long long) * 1024);
+    if (!buf) cudaMalloc(&buf, 16 * sizeof(long long) * 1024);
+    cudaMemset(buf, 0, 16 * sizeof(long long) * 1024);
     p.dbg_times = buf;
   }
 
@@ -450,14 +450,19 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   if (L.p.dbg_times) {
     cudaStreamSynchronize(ctx->stream);
     const int nb = static_cast<int>(L.grid.x);
-    std::vector<long long> h(static_cast<size_t>(nb) * 8);
+    std::vector<long long> h(static_cast<size_t>(nb) * 16);
     cudaMemcpy(h.data(), L.p.dbg_times, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    double a[8] = {0};
-    int cnt[8] = {0};
+    double a[16] = {0}, mx[16] = {0};
+    int cnt[16] = {0};
     for (int b = 0; b < nb; ++b)
-      for (int j = 0; j < 8; ++j)
-        if (h[static_cast<size_t>(b) * 8 + j]) { a[j] += static_cast<double>(h[static_cast<size_t>(b) * 8 + j]); ++cnt[j]; }
-    for (int j = 0; j < 8; ++j) if (cnt[j]) a[j] /= cnt[j];
+      for (int j = 0; j < 16; ++j)
+        if (h[static_cast<size_t>(b) * 16 + j]) {
+          a[j] += static_cast<double>(h[static_cast<size_t>(b) * 16 + j]); ++cnt[j];
+          mx[j] = std::max(mx[j], static_cast<double>(h[static_cast<size_t>(b) * 16 + j]));
+        }
+    for (int j = 0; j < 16; ++j) if (cnt[j]) a[j] /= cnt[j];
+    fprintf(stderr, "[dbg_phases] since kernel entry (mean / max over CTAs): prologue %.0f / %.0f | issuer done %.0f / %.0f | epilogue done %.0f / %.0f | CTA done %.0f / %.0f\n",
+            a[8], mx[8], a[9], mx[9], a[10], mx[10], a[11], mx[11]);
     fprintf(stderr, "[dbg_times] grid %ux%d MT=%d n_tile=%d trips=%d | mma: total %.0f wait_acc %.0f wait_a %.0f wait_b %.0f | "
                     "epi: total %.0f wait_acc_full %.0f | prodA: total %.0f wait_a_empty %.0f (cycles, mean over CTAs)\n",
             L.grid.x, L.p.two ? 2 : 1, L.p.MT, L.p.n_tile, (L.p.n_items + nb / (L.p.two ? 2 : 1) - 1) / (nb / (L.p.two ? 2 : 1)),
