@@ -164,6 +164,69 @@ def cpu_oracle_rate(sample_images: int):
     return sample_images / dt, orc.lib().orc_num_threads(), dt
 
 
+def mnist_config0(ctx=None):
+    """BASELINE configs[0]: MNIST MLP FP32 forward, batch 1024, on the reference's host C path: MN/v3.c forward_timed
+    from oracle/_ref/libref_mnist_v3.so when that was built (kind "reference"), else the oracle restatement (kind
+    "port"); single thread, as the reference is.  With a context, also the INT8 MLP on the GPU (dlq_b200/mnist.py)."""
+    import ctypes as C
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    B, ind, hid, outd = 1024, 784, 256, 10
+    rng = np.random.default_rng(12345)
+    x = ((rng.random((B, ind), dtype=np.float32) - np.float32(0.1307)) / np.float32(0.3081)).astype(np.float32)
+    w1 = (rng.standard_normal((ind, hid)) * np.sqrt(2.0 / ind)).astype(np.float32)
+    w2 = (rng.standard_normal((hid, outd)) * np.sqrt(2.0 / hid)).astype(np.float32)
+    b1, b2 = np.zeros(hid, np.float32), np.zeros(outd, np.float32)
+    out = {"workload": "MNIST MLP 784-256-10 forward, batch 1024, synthetic data (MN/v3.c:99-105 normalisation)"}
+    ref = os.path.join(ROOT, "oracle", "_ref", "libref_mnist_v3.so")
+    hidden, y = np.zeros((B, hid), np.float32), np.zeros((B, outd), np.float32)
+    fp = C.POINTER(C.c_float)
+    reps = 3
+    if os.path.exists(ref):
+        lib = C.CDLL(ref)
+
+        class NN(C.Structure):
+            _fields_ = [(n, fp) for n in ("weights1", "weights2", "bias1", "bias2", "grad_weights1", "grad_weights2",
+                                          "grad_bias1", "grad_bias2")]
+        nn = NN()
+        nn.weights1, nn.weights2 = w1.ctypes.data_as(fp), w2.ctypes.data_as(fp)
+        nn.bias1, nn.bias2 = b1.ctypes.data_as(fp), b2.ctypes.data_as(fp)
+        stats = (C.c_double * 32)()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            lib.forward_timed(C.byref(nn), x.ctypes.data_as(fp), hidden.ctypes.data_as(fp), y.ctypes.data_as(fp), B, stats)
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu"] = {"kind": "reference", "impl": "MN/v3.c forward_timed (unmodified, gcc -O2)", "cores": 1,
+                      "ms_per_forward": dt * 1e3, "images_per_s": B / dt}
+    else:
+        import orc
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            orc.mnist_forward(x, w1, b1, w2, b2)
+        dt = (time.perf_counter() - t0) / reps
+        out["cpu"] = {"kind": "port", "impl": "oracle restatement of MN/v3.c:125-215", "cores": 1,
+                      "ms_per_forward": dt * 1e3, "images_per_s": B / dt}
+    if ctx is not None:
+        import torch
+        from dlq_b200.mnist import MnistMLP
+        m = MnistMLP(ctx, w1, b1, w2, b2, x[:128])
+        dx = torch.from_numpy(x).cuda()
+        stream = torch.cuda.ExternalStream(ctx.stream)
+        for _ in range(5):
+            m.forward(dx)
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(50):
+            m.forward(dx)
+        e1.record(stream)
+        ctx.sync()
+        ms = e0.elapsed_time(e1) / 50
+        out["gpu_int8"] = {"ms_per_forward": ms, "images_per_s": B / (ms * 1e-3),
+                           "how": "INT8 FC operators through the C ABI (6 launches), device-resident input"}
+    return out
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
@@ -353,6 +416,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         except Exception as ex:   # the oracle is a checker; never let it break the product measurement
             cpu = {"value": None, "unit": "images/s", "cores": 0, "kind": "port", "sample": f"unavailable: {ex}"}
 
+    mnist_info = None
+    if world == 1 and not args.no_extras:
+        try:
+            mnist_info = mnist_config0(ctx)
+        except Exception as ex:
+            mnist_info = {"error": str(ex)}
+
     line = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -375,6 +445,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                      "per_launch_ms": {n: round(float(v), 4) for n, v in zip(names, prof)}},
         "cpu_baseline": cpu,
         "e2e_u8": e2e_u8,
+        "mnist_config0": mnist_info,
         "fp8": fp8_info,
         "latency_b1": lat_info,
     }

@@ -6,3 +6,4 @@ pl = r["per_launch_ms"]
 print(" ".join(f"{k.replace('layer','L').replace('downsample','ds').replace('conv','c')}={v*1000:.0f}" for k, v in pl.items()))
 print("fp8:", d.get("fp8"), "| latency_b1:", d.get("latency_b1"))
 print("e2e_u8:", (d.get("e2e_u8") or {}).get("value"))
+print("mnist_config0:", d.get("mnist_config0"))
