@@ -491,6 +491,11 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   const long long t_entry = clock64();
+  if (p.dbg_times && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 12] = static_cast<long long>(gt);     // CTA entry, ns
+  }
   extern __shared__ uint8_t smem_raw[];
   // align to 1024 B with pointer arithmetic on the __shared__ array (keeps the address space visible to
   // the compiler so alpha/beta reads become LDS, not generic loads)
@@ -552,11 +557,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     else { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < p.n_steps; i += blockDim.x) s_step_a16[i] = p.step_a16[i];
-  for (int i = threadIdx.x; i < p.OC; i += blockDim.x) {
-    s_alpha[i] = p.alpha ? p.alpha[i] : 1.f;
-    s_beta[i] = p.beta ? p.beta[i] : 0.f;
-    if (p.fused) { s_alpha2[i] = p.alpha2[i]; s_beta2[i] = p.beta2[i]; }
-  }
+  // (alpha/beta are fetched by the epilogue warps after the CTA-wide sync, off the producers' critical path)
   tc_fence_before();
   __syncthreads();
   if (TWO) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
@@ -713,6 +714,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     uint32_t cs = 0, cph = 0;
     long long t_wait = 0;
     const long long t_begin = clock64();
+    // per-channel constants -> shared memory (kernel-lifetime constants, not produced by the previous kernel), while
+    // the first patch / weight loads and MMAs are in flight; the epilogue warps meet on named barrier 1
+    for (int i = static_cast<int>(threadIdx.x) - 128; i < p.OC; i += n_epi_warps * 32) {
+      s_alpha[i] = p.alpha ? p.alpha[i] : 1.f;
+      s_beta[i] = p.beta ? p.beta[i] : 0.f;
+      if (p.fused) { s_alpha2[i] = p.alpha2[i]; s_beta2[i] = p.beta2[i]; }
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
     pdl_wait();     // the residual is an earlier kernel's output, and our stores must not race its readers
     if (has_res && gid < p.n_items && n_pairs > 0) prefetch_pair(gid, 0);
     for (int it = gid; it < p.n_items; it += G) {
@@ -787,7 +796,12 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   if (p.dbg_times && threadIdx.x == 128) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 10] = clock64() - t_entry;  // first epilogue warp done
   tc_fence_before();
   __syncthreads();
-  if (p.dbg_times && threadIdx.x == 0) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 11] = clock64() - t_entry;    // CTA done
+  if (p.dbg_times && threadIdx.x == 0) {
+    p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 11] = clock64() - t_entry;    // CTA done
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 13] = static_cast<long long>(gt);     // CTA done, ns
+  }
   if (TWO) cluster_sync_all();   // nobody leaves while the peer may still arrive on its barriers / read its smem
   if (warp == 1) {
     if (TWO) tmem_dealloc_pair(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);

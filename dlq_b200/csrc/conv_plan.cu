@@ -461,6 +461,15 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
           mx[j] = std::max(mx[j], static_cast<double>(h[static_cast<size_t>(b) * 16 + j]));
         }
     for (int j = 0; j < 16; ++j) if (cnt[j]) a[j] /= cnt[j];
+    {
+      long long s0 = h[12], s1 = h[12], e0 = h[13], e1 = h[13];
+      for (int b = 0; b < nb; ++b) {
+        s0 = std::min(s0, h[static_cast<size_t>(b) * 16 + 12]); s1 = std::max(s1, h[static_cast<size_t>(b) * 16 + 12]);
+        e0 = std::min(e0, h[static_cast<size_t>(b) * 16 + 13]); e1 = std::max(e1, h[static_cast<size_t>(b) * 16 + 13]);
+      }
+      fprintf(stderr, "[dbg_span] globaltimer ns relative to the first CTA entry: last entry %lld | first exit %lld | last exit %lld\n",
+              s1 - s0, e0 - s0, e1 - s0);
+    }
     fprintf(stderr, "[dbg_phases] since kernel entry (mean / max over CTAs): prologue %.0f / %.0f | issuer done %.0f / %.0f | epilogue done %.0f / %.0f | CTA done %.0f / %.0f\n",
             a[8], mx[8], a[9], mx[9], a[10], mx[10], a[11], mx[11]);
     fprintf(stderr, "[dbg_times] grid %ux%d MT=%d n_tile=%d trips=%d | mma: total %.0f wait_acc %.0f wait_a %.0f wait_b %.0f | "
