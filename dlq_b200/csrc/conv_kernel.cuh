@@ -373,7 +373,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   const int my_swz = (e.lane >> 1) & 3;
 #pragma unroll
   for (int u = 0; u < NU; ++u) my_row[u] = e.slots + u * kEpiStageBytes + e.lane * kEpiStageRow;
-#pragma unroll
+#pragma unroll 1
   for (int h = 0; h < 2; ++h) {
     uint32_t v[NU][32];
 #pragma unroll
