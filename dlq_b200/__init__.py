@@ -44,6 +44,10 @@ ABI_SYMBOLS = [
     "dlq_resnet18_set_preprocess", "dlq_resnet18_forward_u8", "dlq_resnet18_forward_host_u8",
     "dlq_resnet18_checkpoint", "dlq_resnet18_graph_capture", "dlq_resnet18_graph_launch", "dlq_resnet18_launches", "dlq_resnet18_profile", "dlq_synth_fill_f32",
     "dlq_multi_create", "dlq_multi_destroy", "dlq_multi_forward_host", "dlq_multi_last_error_string",
+    "dlq_weight_dir_load", "dlq_weight_dir_weights", "dlq_weight_dir_free", "dlq_weight_dir_save",
+    "dlq_resnet18_f32_create", "dlq_resnet18_f32_destroy", "dlq_resnet18_f32_forward", "dlq_resnet18_f32_checkpoint",
+    "dlq_resnet18_f32_absmax", "dlq_resnet18_f32_reset_absmax", "dlq_act_scales_from_absmax",
+    "dlq_topk_f32", "dlq_compare_f32",
 ]
 
 
@@ -140,6 +144,19 @@ def load_library() -> C.CDLL:
         "dlq_multi_destroy": (None, [vp]),
         "dlq_multi_forward_host": (i, [vp, vp, i, vp]),
         "dlq_multi_last_error_string": (C.c_char_p, [vp]),
+        "dlq_weight_dir_load": (i, [C.c_char_p, C.POINTER(vp), C.c_char_p, sz]),
+        "dlq_weight_dir_weights": (C.POINTER(_ResNet18Weights), [vp]),
+        "dlq_weight_dir_free": (None, [vp]),
+        "dlq_weight_dir_save": (i, [C.c_char_p, C.POINTER(_ResNet18Weights), i]),
+        "dlq_resnet18_f32_create": (i, [vp, C.POINTER(_ResNet18Weights), i, C.POINTER(vp)]),
+        "dlq_resnet18_f32_destroy": (None, [vp]),
+        "dlq_resnet18_f32_forward": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_f32_checkpoint": (i, [vp, C.c_char_p, vp]),
+        "dlq_resnet18_f32_absmax": (i, [vp, vp]),
+        "dlq_resnet18_f32_reset_absmax": (i, [vp]),
+        "dlq_act_scales_from_absmax": (None, [vp, i, vp]),
+        "dlq_topk_f32": (i, [vp, vp, i, i, i, vp, vp]),
+        "dlq_compare_f32": (i, [vp, vp, vp, sz, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -376,6 +393,18 @@ class Context:
         n, k = x.shape
         self._ck(self.lib.dlq_softmax_f32(self.h, _ptr(x), n, k, _ptr(y)))
 
+    def topk_f32(self, x, k: int, idx, val=None):
+        """idx: int32 [N,k] device tensor; val: optional float32 [N,k]"""
+        n, kk = x.shape
+        self._ck(self.lib.dlq_topk_f32(self.h, _ptr(x), n, kk, k, _ptr(idx), _ptr(val)))
+
+    def compare_f32(self, a, b) -> Dict[str, float]:
+        """max_abs / mean_abs / cosine of two equally sized float32 device tensors (R/utils.hpp diff_max_mean +
+        tools/diag_e2e_compare.py cosine)"""
+        out = np.zeros(3, dtype=np.float64)
+        self._ck(self.lib.dlq_compare_f32(self.h, _ptr(a), _ptr(b), a.numel(), out.ctypes.data))
+        return {"max_abs": float(out[0]), "mean_abs": float(out[1]), "cosine": float(out[2])}
+
 
 def _weights_struct(weights: Dict[str, np.ndarray], act_scale, fp8: bool = False) -> tuple:
     """Build the dlq_resnet18_weights struct from a dict keyed like the reference's <key>.bin export
@@ -413,9 +442,14 @@ class ResNet18:
     def __init__(self, ctx: Context, weights: Dict[str, np.ndarray], act_scale, max_batch: int, fp8: bool = False):
         """fp8=True: E4M3 weights / activations with FP32 accumulation (act_scale maps absmax to 448)"""
         self.ctx = ctx
-        s, keep = _weights_struct(weights, act_scale, fp8)
         h = C.c_void_p()
-        ctx._ck(ctx.lib.dlq_resnet18_create(ctx.h, C.byref(s), max_batch, C.byref(h)))
+        if isinstance(weights, WeightDir):       # loaded by the C++ loader; act_scale=None keeps the directory's scales
+            if act_scale is not None:
+                weights.set_act_scale(act_scale, fp8)
+            ctx._ck(ctx.lib.dlq_resnet18_create(ctx.h, weights.struct_ptr, max_batch, C.byref(h)))
+        else:
+            s, keep = _weights_struct(weights, act_scale, fp8)
+            ctx._ck(ctx.lib.dlq_resnet18_create(ctx.h, C.byref(s), max_batch, C.byref(h)))
         self.h = h
         self.max_batch = max_batch
 
@@ -476,6 +510,101 @@ class ResNet18:
         if self.h:
             self.ctx.lib.dlq_resnet18_destroy(self.h)
             self.h = None
+
+
+class ResNet18F32:
+    """The reference's FP32 network on the GPU (bit-exact restatement of its operators): PTQ calibrator and the FP32
+    side of the accuracy harness.  `weights` is a dict keyed like the reference's export, or a WeightDir."""
+
+    CHECKPOINTS = {"stem_pool": (64, 56, 56), "layer1": (64, 56, 56), "layer2": (128, 28, 28), "layer3": (256, 14, 14),
+                   "layer4": (512, 7, 7), "gap": (512,)}     # tools/diag_e2e_compare.py:5-13
+
+    def __init__(self, ctx: Context, weights, max_batch: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        if isinstance(weights, WeightDir):
+            ctx._ck(ctx.lib.dlq_resnet18_f32_create(ctx.h, weights.struct_ptr, max_batch, C.byref(h)))
+        else:
+            s, keep = _weights_struct(weights, np.zeros(NUM_ACTS, np.float32))
+            ctx._ck(ctx.lib.dlq_resnet18_f32_create(ctx.h, C.byref(s), max_batch, C.byref(h)))
+        self.h = h
+        self.max_batch = max_batch
+
+    def forward(self, x, logits):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_forward(self.h, _ptr(x), x.shape[0], _ptr(logits)))
+
+    def checkpoint(self, name: str, out):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_checkpoint(self.h, name.encode(), _ptr(out)))
+
+    def absmax(self) -> np.ndarray:
+        am = np.zeros(NUM_ACTS, dtype=np.float32)
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_absmax(self.h, am.ctypes.data))
+        return am
+
+    def reset_absmax(self):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_reset_absmax(self.h))
+
+    def act_scales(self, fp8: bool = False) -> np.ndarray:
+        """PTQ activation scales from the running absmax (spec/QUANT_SPEC.md 2 / 6)"""
+        am = self.absmax()
+        sc = np.zeros(NUM_ACTS, dtype=np.float32)
+        self.ctx.lib.dlq_act_scales_from_absmax(am.ctypes.data, 1 if fp8 else 0, sc.ctypes.data)
+        return sc
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dlq_resnet18_f32_destroy(self.h)
+            self.h = None
+
+
+class WeightDir:
+    """A weight directory in the reference's export format (<key>.bin, tools/export_resnet18.py:85-92), read by the
+    C++ loader.  No GPU needed."""
+
+    def __init__(self, path: str):
+        self.lib = load_library()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = self.lib.dlq_weight_dir_load(path.encode(), C.byref(h), err, 512)
+        if rc != 0:
+            raise DlqError(rc, err.value.decode())
+        self.h = h
+        self.struct_ptr = self.lib.dlq_weight_dir_weights(h)
+
+    @property
+    def act_scale(self) -> np.ndarray:
+        return np.array(list(self.struct_ptr.contents.act_scale), dtype=np.float32)
+
+    def set_act_scale(self, act_scale, fp8: bool = False):
+        for i in range(NUM_ACTS):
+            self.struct_ptr.contents.act_scale[i] = float(act_scale[i])
+        self.struct_ptr.contents.fp8 = 1 if fp8 else 0
+
+    def tensor(self, field: str, idx: int, n: int) -> np.ndarray:
+        """copy of one tensor, e.g. tensor('conv_w', 0, 64*3*7*7)"""
+        p = getattr(self.struct_ptr.contents, field)
+        p = p[idx] if idx is not None else p
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).copy()
+
+    def save(self, path: str, with_scales: bool = True):
+        rc = self.lib.dlq_weight_dir_save(path.encode(), self.struct_ptr, 1 if with_scales else 0)
+        if rc != 0:
+            raise DlqError(rc, f"cannot write weight directory {path}")
+
+    def close(self):
+        if self.h:
+            self.lib.dlq_weight_dir_free(self.h)
+            self.h = None
+
+
+def save_weight_dir(path: str, weights: Dict[str, np.ndarray], act_scale=None):
+    """Write a dict keyed like the reference's export as <key>.bin + manifest.json through the C++ writer."""
+    lib = load_library()
+    s, keep = _weights_struct(weights, act_scale if act_scale is not None else np.zeros(NUM_ACTS, np.float32))
+    os.makedirs(path, exist_ok=True)
+    rc = lib.dlq_weight_dir_save(path.encode(), C.byref(s), 1 if act_scale is not None else 0)
+    if rc != 0:
+        raise DlqError(rc, f"cannot write weight directory {path}")
 
 
 class MultiGPU:

@@ -209,6 +209,47 @@ int dlq_resnet18_launches(const dlq_resnet18* m);
  * (the reference brackets every launch with its cudaEvent Timer the same way, R/utils.hpp:85-92) */
 int dlq_resnet18_profile(dlq_resnet18* m, const float* x, int N, float* logits, float* ms);
 
+/* ------------------------------------------------------------------ weight directory, PTQ calibration, accuracy
+ * (the stages either side of the hot path)
+ *
+ * Weight directory = the reference's export format (T/export_resnet18.py:85-92): one raw little-endian fp32 file
+ * per state_dict key, "<key>.bin", names as R/infer_e2e.cu:262-330,428-429 reads them.  dlq_weight_dir_load checks
+ * every size like load_bin_f32 (R/utils.hpp:48-60) but reports instead of exiting: returns 1 and fills err.
+ * The returned weights point into the object (valid until dlq_weight_dir_free); act_scale is filled when the
+ * directory carries "quant.act_scale.int8.bin" (written by dlq_weight_dir_save with with_scales = 1 - the "quant"
+ * block RKL/reports/Step1.md:92 plans), else zero: calibrate first. */
+typedef struct dlq_weight_dir dlq_weight_dir;
+int dlq_weight_dir_load(const char* dir, dlq_weight_dir** out, char* err, size_t err_len);
+const dlq_resnet18_weights* dlq_weight_dir_weights(const dlq_weight_dir* d);
+void dlq_weight_dir_free(dlq_weight_dir* d);
+/* writes every tensor of w as <key>.bin plus manifest.json into an existing directory (HOST pointers) */
+int dlq_weight_dir_save(const char* dir, const dlq_resnet18_weights* w, int with_scales);
+
+/* The reference's FP32 network on the GPU, operator for operator and bit for bit (sequential-FMA conv of
+ * K/im2col.cu + K/sgemm_tiled.cu, K/bn_inference.cu:22-27, K/relu.cu:9, K/add.cu:7, K/maxpool2d.cu:14-40,
+ * K/gap_global.cu:10-32, R/infer_e2e.cu:206-219), for batches.  Two uses: (1) PTQ calibration - every forward
+ * folds the absmax of the DLQ_NUM_ACTS activation tensors into a running maximum; (2) the FP32 side of the accuracy
+ * harness (checkpoints named as R/infer_e2e.cu:297-426 dumps them).  Not a hot path (CUDA cores, one thread per
+ * 8 outputs).  x, logits and checkpoint outputs are DEVICE pointers; act_scale of w is ignored. */
+typedef struct dlq_resnet18_f32 dlq_resnet18_f32;
+int dlq_resnet18_f32_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_batch, dlq_resnet18_f32** out);
+void dlq_resnet18_f32_destroy(dlq_resnet18_f32* m);
+int dlq_resnet18_f32_forward(dlq_resnet18_f32* m, const float* x, int N, float* logits);
+/* fp32 NCHW copy of a checkpoint of the LAST forward: "stem_pool","layer1".."layer4","gap" */
+int dlq_resnet18_f32_checkpoint(dlq_resnet18_f32* m, const char* name, float* out);
+/* running absmax since creation / the last reset -> HOST array [DLQ_NUM_ACTS]; synchronises */
+int dlq_resnet18_f32_absmax(dlq_resnet18_f32* m, float* absmax);
+int dlq_resnet18_f32_reset_absmax(dlq_resnet18_f32* m);
+/* spec/QUANT_SPEC.md 2 / 6: act_scale[i] = fp32(absmax[i] / 127) (INT8) or / 448 (E4M3); absmax 0 counts as 1. HOST. */
+void dlq_act_scales_from_absmax(const float* absmax, int fp8, float* act_scale);
+
+/* top-k of every row of x[N,K] (k <= 32): idx[N,k] (and val[N,k] unless NULL), ties to the lower index - the
+ * arg-max R/infer_e2e.cu:436-438 prints, for batches and k > 1.  DEVICE pointers. */
+int dlq_topk_f32(dlq_ctx* ctx, const float* x, int N, int K, int k, int* idx, float* val);
+/* out3 (HOST) = { max |a-b|, mean |a-b|, cosine(a,b) } accumulated in double: diff_max_mean (R/utils.hpp:163-177)
+ * and T/diag_e2e_compare.py:12-24 in one pass over DEVICE tensors.  Synchronises. */
+int dlq_compare_f32(dlq_ctx* ctx, const float* a, const float* b, size_t n, double* out3);
+
 /* deterministic synthetic data: v[i] = (lo + splitmix64(seed,name) % (hi-lo+1)) * 2^-shift. HOST. */
 void dlq_synth_fill_f32(float* v, size_t n, uint64_t seed, const char* name, int lo, int hi, int shift);
 
