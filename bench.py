@@ -395,6 +395,42 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 m1.close()
             except Exception as ex:
                 lat_info = {"error": str(ex)}
+    # ---- accuracy harness on synthetic images: INT8 / FP8 logits vs the reference's FP32 arithmetic
+    # (dlq_resnet18_f32_*, bit-exact restatement of the reference's operators), in-process
+    acc_info = None
+    if not args.no_extras and world == 1:
+        try:
+            na = 32
+            xa = torch.from_numpy(synth.make_input(21, na)).cuda()
+            fnet = dlq_b200.ResNet18F32(ctx, weights, na)
+            lf = torch.empty((na, 1000), dtype=torch.float32, device="cuda")
+            lq = torch.empty((na, 1000), dtype=torch.float32, device="cuda")
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fnet.forward(xa, lf)
+            ev0.record(stream)
+            fnet.forward(xa, lf)
+            ev1.record(stream)
+            ctx.sync()
+            tf = torch.empty((na, 1), dtype=torch.int32, device="cuda")
+            tq = torch.empty((na, 1), dtype=torch.int32, device="cuda")
+            ctx.topk_f32(lf, 1, tf)
+            acc_info = {"images": na, "fp32_reference_arith_images_per_s": na / (ev0.elapsed_time(ev1) * 1e-3),
+                        "how": "logits of the quantised network vs dlq_resnet18_f32_forward on the same synthetic images"}
+            for tag, is8 in (("int8", False), ("fp8", True)):
+                sc = np.asarray(synth.load_act_scales(0), dtype=np.float64)
+                sc = (sc * 127.0 / 448.0).astype(np.float32) if is8 else sc.astype(np.float32)
+                mq = dlq_b200.ResNet18(ctx, weights, sc, na, fp8=is8)
+                mq.forward(xa, lq)
+                r = ctx.compare_f32(lf, lq)
+                ctx.topk_f32(lq, 1, tq)
+                ctx.sync()
+                acc_info[tag] = {"cosine": r["cosine"], "max_abs": r["max_abs"], "mean_abs": r["mean_abs"],
+                                 "agree_top1": float((tf == tq).float().mean().item())}
+                mq.close()
+            fnet.close()
+        except Exception as ex:
+            acc_info = {"error": str(ex)}
+
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv_traffic.json")
     if os.path.exists(tpath):
@@ -448,6 +484,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "mnist_config0": mnist_info,
         "fp8": fp8_info,
         "latency_b1": lat_info,
+        "accuracy_vs_fp32": acc_info,
     }
     print_json(line)
     if dist is not None:
