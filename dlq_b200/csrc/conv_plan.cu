@@ -207,7 +207,10 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       DLQ_ARG(ctx, in.PR >= w->pH, "input tensor needs PR >= pad");
       p.Ho = in.H + 2 * w->pH - w->kH + 1;
       p.Wo = in.W + 2 * w->pW - w->kW + 1;
-      p.Wp = in.W + 2 * w->pW;
+      // virtual row pitch: W + pad, not W + 2 pad - the zero column left of row r+1 doubles as the zero column
+      // right of row r (the patch is one linear run of pixels), exactly as the pad rows are shared between images
+      p.Wp = in.W + (getenv("DLQ_DBG_WIDE_ROWS") ? 2 * w->pW : w->pW);
+      if (p.Wp < p.Wo) p.Wp = p.Wo;
       p.Pv = in.H + in.PR;
       break;
     case CONV_S2_3x3:
