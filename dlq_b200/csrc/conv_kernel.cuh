@@ -52,6 +52,17 @@ __device__ __forceinline__ int epi_stage_off(int row, int chunk) {
 }
 
 
+// Per-role cycle counters (DLQ_DBG_TIMES=1, see conv_plan.cu) exist only in a library built with `make TIMING=1`:
+// in the product build every clock read below is a compile-time 0 and the counter arithmetic disappears from the
+// producer / issuer / epilogue loops.
+__device__ __forceinline__ long long dbg_clock() {
+#ifdef DLQ_TIMING
+  return clock64();
+#else
+  return 0;
+#endif
+}
+
 struct ConvKernelParams {
   // virtual output space
   int Wp, Wo, Ho, Pv, N;
@@ -186,32 +197,32 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
     const int sp = it / c.n_tiles;
     const int g0 = (TWO ? 2 * sp : sp) * c.super_stride;          // (pairs: super_stride % Wp == 0, so in_patch == 0)
     const uint32_t in_patch16 = static_cast<uint32_t>(g0 - (g0 / c.Wp) * c.Wp) * (ROWB / 16);
-    long long tw = clock64();
+    long long tw = dbg_clock();
     if (TWO) mbar_wait_cluster(&c.acc_empty[cs], cph ^ 1u); else mbar_wait(&c.acc_empty[cs], cph ^ 1u);
-    t_acc += clock64() - tw;
+    t_acc += dbg_clock() - tw;
     tc_fence_after();
     const uint32_t d0 = c.tmem_base + cs * c.acc_cols + c.d_off;
     for (int s = 0; s < c.n_sub; ++s) {
-      tw = clock64();
+      tw = dbg_clock();
       mbar_wait(&c.a_full[as], aph);
-      t_a += clock64() - tw;
+      t_a += dbg_clock() - tw;
       tc_fence_after();
       const uint32_t a_base = a_flags + as * c.a_stage16 + in_patch16;
       int k = c.sub_step0[s];
       const int k_end = c.sub_step0[s + 1];
       if (RESIDENT && first_pass) {               // weights arrive once; afterwards no weight barrier at all
         for (int kw = k; kw < k_end; ++kw) {
-          tw = clock64();
+          tw = dbg_clock();
           mbar_wait(&c.b_full[kw], 0u);
-          t_b += clock64() - tw;
+          t_b += dbg_clock() - tw;
         }
         tc_fence_after();
       }
       if (s == 0) {                               // peeled first step of the item: overwrites the accumulators
         if (!RESIDENT) {
-          tw = clock64();
+          tw = dbg_clock();
           mbar_wait(&c.b_full[bs], bph);
-          t_b += clock64() - tw;
+          t_b += dbg_clock() - tw;
           tc_fence_after();
         }
         if (c.leader) {
@@ -227,9 +238,9 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
       }
       for (; k < k_end; ++k) {
         if (!RESIDENT) {
-          tw = clock64();
+          tw = dbg_clock();
           mbar_wait(&c.b_full[bs], bph);
-          t_b += clock64() - tw;
+          t_b += dbg_clock() - tw;
           tc_fence_after();
         }
         if (c.leader) {
@@ -253,9 +264,9 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
       }
-      if (c.dbg & 8) { tw = clock64(); }
+      if (c.dbg & 8) { tw = dbg_clock(); }
       if (c.leader) umma_done<TWO>(&c.a_empty[as]);     // sub-patch stage free
-      if (c.dbg & 8) { __syncwarp(); t_b += clock64() - tw; }
+      if (c.dbg & 8) { __syncwarp(); t_b += dbg_clock() - tw; }
       if (++as == static_cast<uint32_t>(c.a_stages)) { as = 0; aph ^= 1u; }
     }
     if (c.leader) umma_done<TWO>(&c.acc_full[cs]);      // accumulators ready for the epilogue
@@ -490,7 +501,7 @@ __global__ void __launch_bounds__(384, 1)
 conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tmw, const ConvKernelParams p) {
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
-  const long long t_entry = clock64();
+  const long long t_entry = dbg_clock();
   if (p.dbg_times && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -563,23 +574,23 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   if (TWO) cluster_sync_all();   // the peer's barriers are initialised before anyone arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (p.dbg_times && threadIdx.x == 0) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 8] = clock64() - t_entry;   // prologue
+  if (p.dbg_times && threadIdx.x == 0) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 8] = dbg_clock() - t_entry;   // prologue
 
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
     if (elect_one()) {
       uint32_t as = 0, aph = 0;
       long long t_wait = 0;
-      const long long t_begin = clock64();
+      const long long t_begin = dbg_clock();
       pdl_wait();   // activations come from the previous kernel(s); everything above (and the weight loads) does not
       for (int it = gid; it < p.n_items; it += G) {
         const int sp = it / p.n_tiles;
         const int st = TWO ? 2 * sp + rank : sp;
         const int v0 = (st * p.super_stride) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
-          const long long tw = clock64();
+          const long long tw = dbg_clock();
           mbar_wait(&a_empty[as], aph ^ 1u);
-          t_wait += clock64() - tw;
+          t_wait += dbg_clock() - tw;
           uint8_t* dst = sA + static_cast<size_t>(as) * a_stage_bytes;
           if (p.dbg & 4) {
             if (rank == 0) mbar_arrive(&a_full[as]);
@@ -599,7 +610,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       }
       if (p.dbg_times) {
         long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
-        d[6] = clock64() - t_begin; d[7] = t_wait;
+        d[6] = dbg_clock() - t_begin; d[7] = t_wait;
       }
     }
   } else if (warp == 2) {
@@ -651,7 +662,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     c.leader = elect_one();
     c.dbg = p.dbg;
     long long tt[3] = {0, 0, 0};
-    const long long t_begin = clock64();
+    const long long t_begin = dbg_clock();
     if (k_split) {
       constexpr int KA = K32 >= 2 ? 1 : 0, KB = K32 >= 2 ? 2 : 0;   // (K32 == 1 never takes this branch)
       if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
@@ -663,8 +674,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     }
     if (p.dbg_times && c.leader && issuer == 0) {
       long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
-      d[0] = clock64() - t_begin; d[1] = tt[0]; d[2] = tt[1]; d[3] = tt[2];
-      d[9] = clock64() - t_entry;      // issuer done, since kernel entry
+      d[0] = dbg_clock() - t_begin; d[1] = tt[0]; d[2] = tt[1]; d[3] = tt[2];
+      d[9] = dbg_clock() - t_entry;      // issuer done, since kernel entry
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
@@ -713,7 +724,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     };
     uint32_t cs = 0, cph = 0;
     long long t_wait = 0;
-    const long long t_begin = clock64();
+    const long long t_begin = dbg_clock();
     // per-channel constants -> shared memory (kernel-lifetime constants, not produced by the previous kernel), while
     // the first patch / weight loads and MMAs are in flight; the epilogue warps meet on named barrier 1
     for (int i = static_cast<int>(threadIdx.x) - 128; i < p.OC; i += n_epi_warps * 32) {
@@ -729,9 +740,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       const int nt = it - sp * p.n_tiles;
       const int st = TWO ? 2 * sp + rank : sp;
       const uint32_t acc_empty_addr = TWO ? leader_cta_addr(&acc_empty[cs]) : smem_u32(&acc_empty[cs]);
-      const long long tw = clock64();
+      const long long tw = dbg_clock();
       mbar_wait(&acc_full[cs], cph);
-      t_wait += clock64() - tw;
+      t_wait += dbg_clock() - tw;
       tc_fence_after();
       const int np = (p.dbg & 1) ? 0 : n_pairs;
       for (int pi = 0; pi < np; ++pi) {
@@ -790,14 +801,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     if (has_res) cp_async_wait_all();
     if (p.dbg_times && ew == 0 && lane == 0) {
       long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
-      d[4] = clock64() - t_begin; d[5] = t_wait;
+      d[4] = dbg_clock() - t_begin; d[5] = t_wait;
     }
   }
-  if (p.dbg_times && threadIdx.x == 128) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 10] = clock64() - t_entry;  // first epilogue warp done
+  if (p.dbg_times && threadIdx.x == 128) p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 10] = dbg_clock() - t_entry;  // first epilogue warp done
   tc_fence_before();
   __syncthreads();
   if (p.dbg_times && threadIdx.x == 0) {
-    p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 11] = clock64() - t_entry;    // CTA done
+    p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 11] = dbg_clock() - t_entry;    // CTA done
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 13] = static_cast<long long>(gt);     // CTA done, ns

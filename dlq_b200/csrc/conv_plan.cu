@@ -369,12 +369,20 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   if (const char* e = getenv("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
   // DLQ_DBG_TIMES=1: per-CTA cycle counters (MMA warp: total / wait acc_empty / wait a_full / wait b_full;
   // epilogue warp 0: total / wait acc_full; A producer: total / wait a_empty), printed by launch_conv
+#ifndef DLQ_TIMING
+  if (getenv("DLQ_DBG_TIMES")) {
+    static bool told = false;
+    if (!told) fprintf(stderr, "[dlq] DLQ_DBG_TIMES needs a library built with `make -C dlq_b200/csrc clean && make -C dlq_b200/csrc TIMING=1`\n");
+    told = true;
+  }
+#else
   if (getenv("DLQ_DBG_TIMES")) {
     static long long* buf = nullptr;
     if (!buf) cudaMalloc(&buf, 16 * sizeof(long long) * 1024);
     cudaMemset(buf, 0, 16 * sizeof(long long) * 1024);
     p.dbg_times = buf;
   }
+#endif
 
   // ---- TMA descriptor over the row-padded NHWC input: dims (C bytes, W, rows)
   EncodeTiledFn enc = encode_tiled_fn();

@@ -497,7 +497,8 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
     // Fusing the shortcut into conv1 saves a launch and a second pass over the input, but forces one tile per
     // item (two accumulator blocks per tile in TMEM): it wins at small batches (latency), loses at large ones.
-    P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= kFuseMaxBatch;
+    const int fuse_max = getenv("DLQ_DBG_FUSE_MAX") ? atoi(getenv("DLQ_DBG_FUSE_MAX")) : kFuseMaxBatch;   // (tuning)
+    P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= fuse_max;
     if (P->fused[b]) {
       SecondConv sc;
       sc.alpha = m->d_alpha[id]; sc.beta = m->d_beta[id]; sc.relu = 0; sc.out = with_n(m->a_ds[b], N);
