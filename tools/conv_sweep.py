@@ -82,8 +82,12 @@ def main():
         ctx.sync()
         tot = 0.0
         for _ in range(args.iters):
-            flush.zero_()                     # L2 flush between timed iterations (256 MB > 126 MB L2)
-            torch.cuda.synchronize()
+            # L2 flush between timed iterations (256 MB > 126 MB L2), enqueued on the SAME stream right in front of
+            # the first event and without a host synchronisation in between: the conv launch is already queued when
+            # the flush retires, so the interval holds the kernel and not ~9 us of idle-GPU launch latency
+            # (profiles/README.md: globaltimer spans of the CTAs vs event times)
+            with torch.cuda.stream(stream):
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             run()
