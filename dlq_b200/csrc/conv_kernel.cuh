@@ -63,6 +63,16 @@ __device__ __forceinline__ long long dbg_clock() {
 #endif
 }
 
+// tuning switches (ConvKernelParams::dbg) are likewise honoured only by a TIMING build
+__device__ __forceinline__ int dbg_flags(int f) {
+#ifdef DLQ_TIMING
+  return f;
+#else
+  (void)f;
+  return 0;
+#endif
+}
+
 struct ConvKernelParams {
   // virtual output space
   int Wp, Wo, Ho, Pv, N;
@@ -181,7 +191,7 @@ __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_
   }
 }
 
-template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL, bool FP8>
+template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL, bool FP8, bool FUSED = false>
 __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out) {
   constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
   constexpr uint32_t SBO = 8u * ROWB;
@@ -229,14 +239,17 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
           // K-split: the second issuer only accumulates, and only after the first one has issued the overwriting MMA
           if (KSEL == 2) mbar_wait(&c.k_first[cs], cph);
-          if (!(c.dbg & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
+          if (!(dbg_flags(c.dbg) & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
           if (KSEL == 1) mbar_arrive(&c.k_first[cs]);
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
         ++k;
       }
+      uint32_t so_next = c.step_a16[k];           // (the table has spare entries behind the last step)
       for (; k < k_end; ++k) {
+        const uint32_t so = so_next;
+        so_next = c.step_a16[k + 1];              // next step's view offset: its load latency hides behind this step's MMAs
         if (!RESIDENT) {
           tw = dbg_clock();
           mbar_wait(&c.b_full[bs], bph);
@@ -245,11 +258,10 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          const uint32_t so = c.step_a16[k];
-          if (c.fused && (so & kStepSecond)) {
+          if (FUSED && (so & kStepSecond)) {
             // fused second conv: all K slices from the first issuer (no cross-issuer ordering on its accumulator),
             // the first such step overwrites
-            if (KSEL != 2 && !(c.dbg & 2)) {
+            if (KSEL != 2 && !(dbg_flags(c.dbg) & 2)) {
               constexpr int K32 = ROWB / 32;
 #pragma unroll
               for (int kk = 0; kk < K32; ++kk)
@@ -257,16 +269,16 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
                                      (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * kk), idesc,
                                      (k == c.first_second_step && kk == 0) ? 0u : 1u);
             }
-          } else if (!(c.dbg & 2)) {
+          } else if (!(dbg_flags(c.dbg) & 2)) {
             issue_step<ROWB, MYMT, false, TWO, KSEL, FP8>(a_hi, b_hi, a_base + so, b_lo, d0, c.n_tile, idesc);
           }
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
       }
-      if (c.dbg & 8) { tw = dbg_clock(); }
+      if (dbg_flags(c.dbg) & 8) { tw = dbg_clock(); }
       if (c.leader) umma_done<TWO>(&c.a_empty[as]);     // sub-patch stage free
-      if (c.dbg & 8) { __syncwarp(); t_b += dbg_clock() - tw; }
+      if (dbg_flags(c.dbg) & 8) { __syncwarp(); t_b += dbg_clock() - tw; }
       if (++as == static_cast<uint32_t>(c.a_stages)) { as = 0; aph ^= 1u; }
     }
     if (c.leader) umma_done<TWO>(&c.acc_full[cs]);      // accumulators ready for the epilogue
@@ -592,7 +604,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           mbar_wait(&a_empty[as], aph ^ 1u);
           t_wait += dbg_clock() - tw;
           uint8_t* dst = sA + static_cast<size_t>(as) * a_stage_bytes;
-          if (p.dbg & 4) {
+          if (dbg_flags(p.dbg) & 4) {
             if (rank == 0) mbar_arrive(&a_full[as]);
           } else if (TWO) {
             // the rank-0 producer alone arrives, expecting BOTH CTAs' bytes; the peer's TMA completes its
@@ -665,7 +677,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     const long long t_begin = dbg_clock();
     if (k_split) {
       constexpr int KA = K32 >= 2 ? 1 : 0, KB = K32 >= 2 ? 2 : 0;   // (K32 == 1 never takes this branch)
-      if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
+      if (p.fused) {      // (the fused shortcut conv forces one tile per item, hence this branch)
+        if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8, true>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8, true>(c, tt); }
+        else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8, true>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8, true>(c, tt); }
+      } else if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
       else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8>(c, tt); }
     } else if (p.b_resident) {
       if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0, FP8>(c, tt);
@@ -744,7 +759,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       mbar_wait(&acc_full[cs], cph);
       t_wait += dbg_clock() - tw;
       tc_fence_after();
-      const int np = (p.dbg & 1) ? 0 : n_pairs;
+      const int np = (dbg_flags(p.dbg) & 1) ? 0 : n_pairs;
       for (int pi = 0; pi < np; ++pi) {
         uint32_t taddr[2];
         int c0[2], g_own[2];
