@@ -315,10 +315,11 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       p.b_stages = p.n_steps;
     } else {
       const size_t left = budget > static_cast<size_t>(min_a) * p.sub_bytes ? budget - static_cast<size_t>(min_a) * p.sub_bytes : 0;
-      p.b_stages = static_cast<int>(std::min<size_t>(std::min(p.n_steps, 8), left / b_stage_bytes));
+      const int b_cap = getenv("DLQ_DBG_B_CAP") ? atoi(getenv("DLQ_DBG_B_CAP")) : 8;     // (tuning)
+      p.b_stages = static_cast<int>(std::min<size_t>(std::min(p.n_steps, b_cap), left / b_stage_bytes));
     }
     const size_t b_bytes = static_cast<size_t>(std::max(p.b_stages, 0)) * b_stage_bytes;
-    const int want_a = std::min(4, p.n_sub + 2);
+    const int want_a = std::min(getenv("DLQ_DBG_A_CAP") ? atoi(getenv("DLQ_DBG_A_CAP")) : 4, p.n_sub + 2);
     const int fit_a = budget > b_bytes ? static_cast<int>((budget - b_bytes) / p.sub_bytes) : 0;
     p.a_stages = std::min(want_a, fit_a);
     if ((p.a_stages >= 2 && p.b_stages >= std::min(p.n_steps, 3) && es * NR <= 256) || MT == 1) break;
