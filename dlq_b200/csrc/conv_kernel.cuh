@@ -248,8 +248,11 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
       }
       uint32_t so_next = c.step_a16[k];           // (the table has spare entries behind the last step)
       for (; k < k_end; ++k) {
-        const uint32_t so = so_next;
-        so_next = c.step_a16[k + 1];              // next step's view offset: its load latency hides behind this step's MMAs
+        // next step's view offset: its load latency hides behind this step's MMAs.  Not for the stem (ROWB 32, two
+        // short MMAs per step): there the faster issue measurably slows the kernel (107.5 -> 112.5 us), the epilogue
+        // being what bounds it
+        const uint32_t so = ROWB == 32 ? static_cast<uint32_t>(c.step_a16[k]) : so_next;
+        if (ROWB != 32) so_next = c.step_a16[k + 1];
         if (!RESIDENT) {
           tw = dbg_clock();
           mbar_wait(&c.b_full[bs], bph);
