@@ -560,13 +560,17 @@ __global__ void maxpool_nchw_i8_kernel(const int8_t* __restrict__ x, int8_t* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// GAP + FC fused (network tail).  One CTA handles IMG images: phase 1 sums the HxW pixels of each
-// channel (int32, exact), scales and requantises to int8 in smem; phase 2 streams the int8 FC weights
-// once per CTA, each warp producing one output row for all IMG images with dp4a + warp shuffles.
+// GAP + FC fused (network tail).  A CTA handles kGapImgs images and one of kGapOSplit slices of the outputs:
+// phase 1 sums the HxW pixels of each channel (int32, exact), scales and requantises to int8 in smem; phase 2
+// streams its slice of the int8 FC weights once, each thread producing one output for all its images with dp4a.
+// The kernel is latency-bound (20 us at batch 256 for 6 MB of activations and 0.5 MB of weights): 4 images per CTA
+// to cut the weights' L2 -> SM traffic was slower (24 us); the output split keeps every thread at one output and
+// halves the serial FC rounds of the batch-1 path.
 // (semantics: K/gap_global.cu:10-32 mean, R/infer_e2e.cu:206-219 FC + bias; arithmetic QUANT_SPEC §5)
 // ------------------------------------------------------------------------------------------------
 constexpr int kGapImgs = 2;
 constexpr int kGapParts = 4;
+constexpr int kGapOSplit = 2;
 __global__ void __launch_bounds__(512)
 gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
               float inv_gap_scale, const int8_t* __restrict__ fc_w, const float* __restrict__ fc_scale,
@@ -610,7 +614,7 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
     for (int pt = 0; pt < kGapParts; ++pt) s += part_sum[(im * kGapParts + pt) * C + c];
     const int q = quant_rn(__fmul_rn(__fmul_rn((float)s, scale_over_hw), inv_gap_scale), -128, 127);
     sg[im * C + c] = static_cast<int8_t>(q);
-    if (gap_q) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
+    if (gap_q && blockIdx.y == 0) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
   }
   __syncthreads();
   if (!logits) return;
@@ -618,7 +622,9 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
   // consecutive threads (= consecutive outputs) read consecutive 16-byte chunks; the pooled activations are
   // broadcast from shared memory.  One thread = one output row for all images of the CTA, no shuffles.
   const int Opad = (O + 63) & ~63;
-  for (int o = threadIdx.x; o < O; o += blockDim.x) {
+  const int o_per = (O + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
+  const int o_end = min(O, (static_cast<int>(blockIdx.y) + 1) * o_per);
+  for (int o = static_cast<int>(blockIdx.y) * o_per + threadIdx.x; o < o_end; o += blockDim.x) {
     int acc[kGapImgs];
 #pragma unroll
     for (int im = 0; im < kGapImgs; ++im) acc[im] = 0;
@@ -864,7 +870,7 @@ int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_s
   DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
   const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
   const size_t gap_smem = static_cast<size_t>(kGapImgs) * kGapParts * in.C * 4 + static_cast<size_t>(kGapImgs) * in.C;
-  DLQ_CUDA(ctx, launch_pdl(gap_fc_kernel, dim3(blocks), dim3(512), gap_smem, ctx->stream, static_cast<const int8_t*>(in.ptr),
+  DLQ_CUDA(ctx, launch_pdl(gap_fc_kernel, dim3(blocks, logits ? kGapOSplit : 1), dim3(512), gap_smem, ctx->stream, static_cast<const int8_t*>(in.ptr),
                            in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits));
   return DLQ_OK;
 }
