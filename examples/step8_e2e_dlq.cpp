@@ -11,10 +11,18 @@
 //                 [--fp32]                              the reference's FP32 arithmetic (dlq_resnet18_f32_*)
 //                 [--compare]                           run FP32 too and print per-checkpoint max_abs / mean_abs /
 //                                                       cosine (tools/diag_e2e_compare.py) and top-1 agreement
-// Exit codes follow the reference (runtime/utils.hpp:23-45): 1 = bad usage / IO, 3 = CUDA error.
+//                 [--expect_dir E] [--atol 1e-4]        parity-test mode, like the reference's per-step drivers
+//                                                       (runtime/infer_layer1.cu:243,287, infer_head.cu:125-132):
+//                                                       compare every checkpoint this run dumped with E/<name>.bin
+//                                                       (a --dump_dir of the reference binary or of another run),
+//                                                       criterion max_abs / max(1, max|expected|) <= atol; exit 2 on
+//                                                       mismatch
+// Exit codes follow the reference (runtime/utils.hpp:23-45, infer_conv1_bn1_relu.cu:150-156): 1 = bad usage / IO,
+// 2 = parity mismatch (--expect_dir), 3 = CUDA error.
 // Host code only: plain C++ against include/dlq.h and the CUDA runtime (device buffers); no kernels here.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -71,11 +79,12 @@ static bool write_f32(const std::string& path, const std::vector<float>& v) {
 
 static void usage() {
   std::cerr << "usage: step8_e2e_dlq --manifest <weight dir> --input <input.bin> [--dump_dir D] [--calib calib.bin]\n"
-               "                     [--save_scales] [--fp8] [--fp32] [--compare]\n";
+               "                     [--save_scales] [--fp8] [--fp32] [--compare] [--expect_dir E [--atol 1e-4]]\n";
 }
 
 int main(int argc, char** argv) {
-  std::string mani, input_path, dump_dir, calib_path;
+  std::string mani, input_path, dump_dir, calib_path, expect_dir;
+  double atol = 1e-4;
   bool fp8 = false, fp32 = false, compare = false, save_scales = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
@@ -83,12 +92,15 @@ int main(int argc, char** argv) {
     else if (a == "--input" && i + 1 < argc) input_path = argv[++i];
     else if (a == "--dump_dir" && i + 1 < argc) dump_dir = argv[++i];
     else if (a == "--calib" && i + 1 < argc) calib_path = argv[++i];
+    else if (a == "--expect_dir" && i + 1 < argc) expect_dir = argv[++i];
+    else if (a == "--atol" && i + 1 < argc) atol = std::atof(argv[++i]);
     else if (a == "--fp8") fp8 = true;
     else if (a == "--fp32") fp32 = true;
     else if (a == "--compare") compare = true;
     else if (a == "--save_scales") save_scales = true;
   }
   if (mani.empty() || input_path.empty()) { usage(); return 1; }
+  if (!expect_dir.empty() && dump_dir.empty()) { std::cerr << "--expect_dir compares the files of --dump_dir: give both\n"; return 1; }
   // the reference takes the directory; accept a path to its manifest.json as well
   if (mani.size() > 13 && mani.substr(mani.size() - 13) == "manifest.json") mani = mani.substr(0, mani.size() - 14);
 
@@ -234,9 +246,39 @@ int main(int argc, char** argv) {
     std::cout << "[E2E] top-1 class index = " << top << ", logit=" << best << "\n";
   }
 
+  // ---- parity-test mode: this run's dumps against an expected dump directory (host-side, diff_max_mean of
+  // runtime/utils.hpp:163-177)
+  int mismatches = 0;
+  if (!expect_dir.empty()) {
+    const char* names[7] = {"stem_pool", "layer1", "layer2", "layer3", "layer4", "gap", "logits"};
+    for (const char* nm : names) {
+      std::vector<float> got, want;
+      std::ifstream probe(dump_dir + "/" + nm + ".bin", std::ios::binary);
+      if (!probe) continue;                                   // (FP8 runs dump logits only)
+      probe.close();
+      if (!read_f32(dump_dir + "/" + nm + ".bin", got, 1) || !read_f32(expect_dir + "/" + nm + ".bin", want, 1)) return 1;
+      if (got.size() != want.size()) {
+        std::cerr << "unexpected size: " << nm << ".bin got " << got.size() << " expected " << want.size() << "\n";
+        return 1;
+      }
+      double max_abs = 0, mean_abs = 0, ref_max = 0;
+      for (size_t i = 0; i < got.size(); ++i) {
+        const double d = std::abs(static_cast<double>(got[i]) - static_cast<double>(want[i]));
+        if (d > max_abs) max_abs = d;
+        mean_abs += d;
+        if (std::abs(static_cast<double>(want[i])) > ref_max) ref_max = std::abs(static_cast<double>(want[i]));
+      }
+      mean_abs /= static_cast<double>(got.size());
+      const bool ok = max_abs / (ref_max > 1.0 ? ref_max : 1.0) <= atol;
+      printf("%s %-10s max_abs=%.6g mean_abs=%.6g (atol %.3g, scale %.4g)\n", ok ? "[OK]  " : "[FAIL]", nm, max_abs, mean_abs,
+             atol, ref_max > 1.0 ? ref_max : 1.0);
+      mismatches += ok ? 0 : 1;
+    }
+  }
+
   if (f32net) dlq_resnet18_f32_destroy(f32net);
   cudaFree(dX); cudaFree(dLogits); cudaFree(dLogitsF); cudaFree(dCkF); cudaFree(dCkQ); cudaFree(dCk8);
   dlq_destroy(ctx);
   dlq_weight_dir_free(wd);
-  return 0;
+  return mismatches ? 2 : 0;
 }

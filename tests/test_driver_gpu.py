@@ -93,6 +93,25 @@ def test_driver_side_by_side_with_reference_binary(workdir):
     assert "agree_top1=1 (100.00%)" in s_i8 and "cosine=" in s_i8
 
 
+def test_driver_parity_mode_exit_codes(workdir):
+    """--expect_dir: the reference's test-binary convention (exit 0 = within atol, exit 2 = mismatch).  The FP32
+    arithmetic passes against the reference binary's own dump at the reference's 1e-4; the INT8 path, compared at
+    that FP32 criterion, is reported as a mismatch - and passes at a quantisation-sized tolerance."""
+    if not os.path.exists(REF_E2E):
+        pytest.skip("oracle/_ref/step8_e2e not built")
+    d, _ = workdir
+    args = ["--manifest", str(d / "w"), "--input", str(d / "input1.bin")]
+    _run([REF_E2E] + args + ["--dump_dir", str(d / "refp")], d)
+    r = subprocess.run([DRV] + args + ["--fp32", "--dump_dir", str(d / "p32"), "--expect_dir", str(d / "refp")],
+                       capture_output=True, text=True, cwd=str(d), timeout=300)
+    assert r.returncode == 0 and r.stdout.count("[OK]") == 7 and "[FAIL]" not in r.stdout, r.stdout + r.stderr
+    q = [DRV] + args + ["--calib", str(d / "calib.bin"), "--dump_dir", str(d / "p8"), "--expect_dir", str(d / "refp")]
+    r = subprocess.run(q, capture_output=True, text=True, cwd=str(d), timeout=300)
+    assert r.returncode == 2 and "[FAIL]" in r.stdout, r.stdout + r.stderr
+    r = subprocess.run(q + ["--atol", "0.1"], capture_output=True, text=True, cwd=str(d), timeout=300)
+    assert r.returncode == 0 and r.stdout.count("[OK]") == 7, r.stdout + r.stderr
+
+
 def test_driver_usage_and_io_errors(workdir):
     d, _ = workdir
     assert subprocess.run([DRV], capture_output=True).returncode == 1                       # usage -> 1 (R/infer_e2e.cu:241)
