@@ -120,3 +120,33 @@ def test_driver_usage_and_io_errors(workdir):
     (d / "short.bin").write_bytes(b"\0" * 4000)
     r = subprocess.run([DRV, "--manifest", str(d / "w"), "--input", str(d / "short.bin")], capture_output=True, text=True)
     assert r.returncode == 1 and "unexpected size" in r.stderr
+
+
+def test_cpp_bench_driver(ctx):
+    """examples/dlq_bench: synthetic weights generated and PTQ-calibrated in C++ (the committed scales, bit for bit),
+    then timed forwards; its top-1 for image 0 equals the ctypes mirror's on the same synthetic image"""
+    import json
+    import torch
+    import dlq_b200
+    exe = os.path.join(ROOT, "examples", "_build", "dlq_bench")
+    if not os.path.exists(exe):
+        pytest.skip("examples/_build/dlq_bench not built (make -C examples)")
+    out = subprocess.run([exe, "--batch", "8", "--iters", "3", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["n_gpus"] == 1 and d["batch"] == 8 and d["images_per_s"] > 0 and d["host_images_per_s"] > 0
+    assert 50 < d["latency_b1_us"] < 5000 and d["launches_per_forward"] == 23
+    w = synth.make_weights(0)
+    m = dlq_b200.ResNet18(ctx, w, synth.load_act_scales(0), 8)
+    dl = torch.empty((8, 1000), dtype=torch.float32, device="cuda")
+    m.forward(torch.from_numpy(synth.make_input(0, 8)).cuda(), dl)
+    ctx.sync()
+    assert d["top1_image0"] == int(dl[0].argmax().item())
+    m.close()
+    if torch.cuda.device_count() >= 2:
+        out = subprocess.run([exe, "--batch", "16", "--iters", "2", "--warmup", "1", "--gpus", "2"], capture_output=True,
+                             text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        d2 = json.loads(out.stdout.strip().splitlines()[-1])
+        assert d2["n_gpus"] == 2 and d2["batch_per_gpu"] == 8 and d2["top1_image0"] == d["top1_image0"]
+    assert subprocess.run([exe, "--bogus"], capture_output=True).returncode == 1
