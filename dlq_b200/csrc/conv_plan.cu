@@ -267,7 +267,8 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       const int srow = in.PR + subs[s].row_off_rel, scol = subs[s].col0;
       const int pr = srow & 1, pc = scol & 1;
       p.sub_col0[s] = static_cast<int16_t>((scol - pc) / 2);
-      DLQ_ARG(ctx, (pr * 2 + pc) * rows_half + (srow >> 1) < 32768, "tensor too tall for 16-bit plane row offsets");
+      // (the plane's first row is a 32-bit field of its own; only the offset inside the plane is 16-bit)
+      DLQ_ARG(ctx, (srow >> 1) < 32768, "sub-patch row offset does not fit 16 bits");
       p.sub_row_off[s] = static_cast<int16_t>(srow >> 1);
       p.sub_plane_row[s] = (pr * 2 + pc) * rows_half;
     } else {

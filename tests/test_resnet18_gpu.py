@@ -78,6 +78,27 @@ def test_batch256_is_image_independent(ctx, model256):
     assert np.array_equal(got2["logits"].view(np.uint32), g["logits"].view(np.uint32))
 
 
+def test_batch1024_is_image_independent(ctx):
+    """BASELINE config 4 per-GPU batch (2048 images over 2 GPUs): parity-plane tensors taller than 32768 rows, image
+    positions past 2^23 - every image's logits still equal what the image produces alone"""
+    import torch
+    import dlq_b200
+    g = np.load(os.path.join(GOLD, "i8_seed0_n2.npz"))
+    x2 = torch.from_numpy(synth.make_input(0, 2)).cuda()
+    n = 1024
+    pick = torch.tensor([(i * 5 + i // 7) % 2 for i in range(n)], device="cuda")
+    x = x2[pick].contiguous()
+    m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    m.forward(x, dl)
+    ctx.sync()
+    want = torch.from_numpy(g["logits"]).cuda()[pick]
+    assert torch.equal(dl.view(torch.int32), want.view(torch.int32))
+    m.close()
+    del x, dl
+    torch.cuda.empty_cache()
+
+
 def test_forward_host_and_quantised_accuracy(ctx, model256):
     """Host-buffer entry point; and the INT8 logits track the FP32 oracle (reported tolerance: cosine)."""
     import torch
