@@ -8,3 +8,4 @@ print("fp8:", d.get("fp8"), "| latency_b1:", d.get("latency_b1"))
 print("e2e_u8:", (d.get("e2e_u8") or {}).get("value"))
 print("mnist_config0:", d.get("mnist_config0"))
 print("accuracy_vs_fp32:", d.get("accuracy_vs_fp32"))
+print("batch_1024:", d.get("batch_1024"))
