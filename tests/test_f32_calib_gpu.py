@@ -150,3 +150,32 @@ def test_int8_tracks_fp32(ctx):
     ctx.sync()
     assert (tf == tq).float().mean().item() >= 0.75
     f.close(); q.close()
+
+
+def test_error_codes(ctx):
+    """bad arguments return 1 with a message (the reference's usage / IO exit code), never abort"""
+    import torch
+    import dlq_b200
+    w = synth.make_weights(0)
+    f = dlq_b200.ResNet18F32(ctx, w, 2)
+    x = torch.zeros((3, 3, 224, 224), dtype=torch.float32, device="cuda")
+    l = torch.zeros((3, 1000), dtype=torch.float32, device="cuda")
+    with pytest.raises(dlq_b200.DlqError) as e:
+        f.forward(x, l)                                   # batch 3 > max_batch 2
+    assert e.value.code == 1 and "max_batch" in str(e.value)
+    with pytest.raises(dlq_b200.DlqError) as e:
+        f.checkpoint("layer1", l)                         # no forward has run yet
+    assert e.value.code == 1
+    f.forward(x[:2].contiguous(), l[:2])
+    with pytest.raises(dlq_b200.DlqError) as e:
+        f.checkpoint("layer9", l)
+    assert e.value.code == 1 and "unknown checkpoint" in str(e.value)
+    idx = torch.zeros((3, 40), dtype=torch.int32, device="cuda")
+    with pytest.raises(dlq_b200.DlqError) as e:
+        ctx.topk_f32(l, 40, idx)                          # k > 32
+    assert e.value.code == 1
+    bad = dict(w)
+    del bad["layer2.0.downsample.0.weight"]
+    with pytest.raises((dlq_b200.DlqError, KeyError)):
+        dlq_b200.ResNet18F32(ctx, bad, 2)
+    f.close()
