@@ -16,6 +16,7 @@ Reference surface mirrored here (yeontachi/DLQ, CUDA/resnet18-kernel-lab/cpp/fp3
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import os
 from typing import Dict, Optional
 
@@ -48,6 +49,14 @@ ABI_SYMBOLS = [
     "dlq_resnet18_f32_create", "dlq_resnet18_f32_destroy", "dlq_resnet18_f32_forward", "dlq_resnet18_f32_checkpoint",
     "dlq_resnet18_f32_absmax", "dlq_resnet18_f32_reset_absmax", "dlq_act_scales_from_absmax",
     "dlq_topk_f32", "dlq_compare_f32",
+    "dlq_workspace_reserve", "dlq_workspace_bytes", "dlq_conv2d_workspace_bytes",
+    "dlq_fc_weights_pack", "dlq_fc_weights_pack_i8", "dlq_fc_weights_pack_e4m3", "dlq_fc_workspace_bytes",
+    "dlq_fc_forward_i8_tc", "dlq_fc_forward_fp8",
+    "dlq_resnet18_submit_host", "dlq_resnet18_submit_host_u8", "dlq_resnet18_wait", "dlq_resnet18_launches_for_batch",
+    "dlq_resnet18_enable_stamps", "dlq_resnet18_read_stamps",
+    "dlq_multi_n_devices", "dlq_multi_set_preprocess", "dlq_multi_forward_host_u8", "dlq_multi_submit_host",
+    "dlq_multi_submit_host_u8", "dlq_multi_wait", "dlq_multi_forward_device",
+    "dlq_mlp_create", "dlq_mlp_destroy", "dlq_mlp_forward", "dlq_mlp_checkpoint", "dlq_mlp_weight_scales",
 ]
 
 
@@ -157,6 +166,33 @@ def load_library() -> C.CDLL:
         "dlq_act_scales_from_absmax": (None, [vp, i, vp]),
         "dlq_topk_f32": (i, [vp, vp, i, i, i, vp, vp]),
         "dlq_compare_f32": (i, [vp, vp, vp, sz, vp]),
+        "dlq_workspace_reserve": (i, [vp, sz]),
+        "dlq_workspace_bytes": (sz, [vp]),
+        "dlq_conv2d_workspace_bytes": (sz, [vp, i, i, i, i, i]),
+        "dlq_fc_weights_pack": (i, [vp, vp, i, i, i, vp, C.POINTER(vp)]),
+        "dlq_fc_weights_pack_i8": (i, [vp, vp, i, i, C.POINTER(vp)]),
+        "dlq_fc_weights_pack_e4m3": (i, [vp, vp, i, i, C.POINTER(vp)]),
+        "dlq_fc_workspace_bytes": (sz, [vp, i]),
+        "dlq_fc_forward_i8_tc": (i, [vp, vp, vp, vp, vp, i, vp]),
+        "dlq_fc_forward_fp8": (i, [vp, vp, vp, vp, vp, i, vp]),
+        "dlq_resnet18_submit_host": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_submit_host_u8": (i, [vp, vp, i, vp]),
+        "dlq_resnet18_wait": (i, [vp]),
+        "dlq_resnet18_launches_for_batch": (i, [vp, i]),
+        "dlq_resnet18_enable_stamps": (i, [vp, i]),
+        "dlq_resnet18_read_stamps": (i, [vp, vp, C.POINTER(i)]),
+        "dlq_multi_n_devices": (i, [vp]),
+        "dlq_multi_set_preprocess": (i, [vp, vp, vp]),
+        "dlq_multi_forward_host_u8": (i, [vp, vp, i, vp]),
+        "dlq_multi_submit_host": (i, [vp, vp, i, vp]),
+        "dlq_multi_submit_host_u8": (i, [vp, vp, i, vp]),
+        "dlq_multi_wait": (i, [vp]),
+        "dlq_multi_forward_device": (i, [vp, C.POINTER(vp), C.POINTER(i), C.POINTER(vp)]),
+        "dlq_mlp_create": (i, [vp, vp, vp, vp, vp, i, i, i, f, f, i, i, C.POINTER(vp)]),
+        "dlq_mlp_destroy": (None, [vp]),
+        "dlq_mlp_forward": (i, [vp, vp, i, vp, vp]),
+        "dlq_mlp_checkpoint": (i, [vp, C.c_char_p, vp]),
+        "dlq_mlp_weight_scales": (i, [vp, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -212,8 +248,22 @@ class ConvWeights:
             pass
 
 
+# Context methods that launch kernels reading / writing caller tensors (ordered after torch's stream, see Context)
+_ORDERED_METHODS = frozenset([
+    "quantize_f32_i8", "dequantize_i8_f32", "dequantize_i8_f32_per_channel", "quantize_f32_e4m3", "dequantize_e4m3_f32",
+    "conv2d_fp8", "conv2d_i8", "conv2d_i8_act", "conv_plan", "act_from_nchw_i8", "act_to_nchw_i8", "stem_pack_input_i8",
+    "bn_inference_f32", "relu_forward_f32", "relu_forward_i8", "add_inplace_f32", "add_requant_i8",
+    "maxpool2d_3x3_s2p1_nchw_i8", "gap_global_i8", "fc_forward_i8", "fc_forward_i8_tc", "fc_forward_fp8", "softmax_f32",
+    "topk_f32", "compare_f32",
+])
+
+
 class Context:
-    """One per device; enqueues on its own stream (see dlq.h)."""
+    """One per device; enqueues on its own NON-BLOCKING stream (see dlq.h), which has no implicit ordering with torch's
+    streams.  Tensors made by torch (`torch.zeros`, `.cuda()`, ...) are produced on torch's current stream, so every
+    call of this mirror first makes the library's stream wait for torch's current stream (`order_after_torch`, an event
+    record + stream wait; a few microseconds of host time).  A timing loop whose buffers are already complete switches
+    that off with `auto_order = False`."""
 
     def __init__(self, device: int = 0):
         self.lib = load_library()
@@ -223,6 +273,17 @@ class Context:
             raise DlqError(rc, f"dlq_create(device={device}) failed: no usable sm_100 GPU (there is no CPU fallback)")
         self.h = h
         self.device = device
+        self.auto_order = True
+        self._ext = None
+
+    def order_after_torch(self):
+        """work enqueued by the library from here on runs after everything torch has enqueued on its current stream"""
+        if not self.auto_order:
+            return
+        import torch
+        if self._ext is None:
+            self._ext = torch.cuda.ExternalStream(self.stream, device=self.device)
+        self._ext.wait_stream(torch.cuda.current_stream(self.device))
 
     def close(self):
         if self.h:
@@ -322,6 +383,7 @@ class Context:
         import torch
         nbytes = self.lib.dlq_act_bytes(n, h, w, c, pr)
         buf = torch.zeros(nbytes + 1024, dtype=torch.int8, device=f"cuda:{self.device}")
+        self.order_after_torch()      # the zero fill runs on torch's stream
         return buf, _Act(buf.data_ptr(), n, h, w, c, pr)
 
     def required_pad_rows(self, w: ConvWeights) -> int:
@@ -389,6 +451,44 @@ class Context:
         o = w.shape[0]
         self._ck(self.lib.dlq_fc_forward_i8(self.h, _ptr(g), _ptr(w), _ptr(scale), _ptr(bias), n, o, i, _ptr(logits)))
 
+    # ---- tensor-core FC (the conv core as a 1x1 convolution), SURVEY 8f-4
+    def pack_fc_weights(self, w_oi: np.ndarray, fp8: bool = False) -> ConvWeights:
+        """w_oi: float32 [O, I] (the reference's fc.weight layout); per-row quantisation, QUANT_SPEC 1 / 6"""
+        w = np.ascontiguousarray(w_oi, dtype=np.float32)
+        o, i_ = w.shape
+        scale = np.empty(o, dtype=np.float32)
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_fc_weights_pack(self.h, w.ctypes.data, o, i_, 1 if fp8 else 0, scale.ctypes.data, C.byref(h)))
+        return ConvWeights(self, h, scale, o)
+
+    def pack_fc_weights_i8(self, wq_oi: np.ndarray) -> ConvWeights:
+        w = np.ascontiguousarray(wq_oi, dtype=np.int8)
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_fc_weights_pack_i8(self.h, w.ctypes.data, w.shape[0], w.shape[1], C.byref(h)))
+        return ConvWeights(self, h, None, w.shape[0])
+
+    def pack_fc_weights_e4m3(self, wq_oi: np.ndarray) -> ConvWeights:
+        w = np.ascontiguousarray(wq_oi, dtype=np.uint8)
+        h = C.c_void_p()
+        self._ck(self.lib.dlq_fc_weights_pack_e4m3(self.h, w.ctypes.data, w.shape[0], w.shape[1], C.byref(h)))
+        return ConvWeights(self, h, None, w.shape[0])
+
+    def fc_forward_i8_tc(self, g, w: ConvWeights, scale, bias, logits):
+        self._ck(self.lib.dlq_fc_forward_i8_tc(self.h, _ptr(g), w.handle, _ptr(scale), _ptr(bias), g.shape[0], _ptr(logits)))
+
+    def fc_forward_fp8(self, g, w: ConvWeights, scale, bias, logits):
+        self._ck(self.lib.dlq_fc_forward_fp8(self.h, _ptr(g), w.handle, _ptr(scale), _ptr(bias), g.shape[0], _ptr(logits)))
+
+    def workspace_reserve(self, nbytes: int):
+        self._ck(self.lib.dlq_workspace_reserve(self.h, nbytes))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.dlq_workspace_bytes(self.h))
+
+    def conv2d_workspace_bytes(self, w: ConvWeights, n, h, w_, has_residual=False, want_acc=False) -> int:
+        return int(self.lib.dlq_conv2d_workspace_bytes(w.handle, n, h, w_, int(has_residual), int(want_acc)))
+
     def softmax_f32(self, x, y):
         n, k = x.shape
         self._ck(self.lib.dlq_softmax_f32(self.h, _ptr(x), n, k, _ptr(y)))
@@ -404,6 +504,18 @@ class Context:
         out = np.zeros(3, dtype=np.float64)
         self._ck(self.lib.dlq_compare_f32(self.h, _ptr(a), _ptr(b), a.numel(), out.ctypes.data))
         return {"max_abs": float(out[0]), "mean_abs": float(out[1]), "cosine": float(out[2])}
+
+
+def _ordered(fn):
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        self.order_after_torch()
+        return fn(self, *args, **kwargs)
+    return wrapper
+
+
+for _name in _ORDERED_METHODS:
+    setattr(Context, _name, _ordered(getattr(Context, _name)))
 
 
 def _weights_struct(weights: Dict[str, np.ndarray], act_scale, fp8: bool = False) -> tuple:
@@ -454,7 +566,38 @@ class ResNet18:
         self.max_batch = max_batch
 
     def forward(self, x, logits):
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_forward(self.h, _ptr(x), x.shape[0], _ptr(logits)))
+
+    @staticmethod
+    def _hp(t):
+        return t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data
+
+    def submit_host(self, x_host, logits_host):
+        """pipelined form: enqueue H2D -> forward -> D2H and return (at most two in flight); pair with wait()"""
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_submit_host(self.h, self._hp(x_host), x_host.shape[0], self._hp(logits_host)))
+
+    def submit_host_u8(self, x_hwc_host, logits_host):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_submit_host_u8(self.h, self._hp(x_hwc_host), x_hwc_host.shape[0],
+                                                              self._hp(logits_host)))
+
+    def wait(self):
+        """block until the oldest outstanding submit's logits are in host memory"""
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_wait(self.h))
+
+    def launches_for_batch(self, n: int) -> int:
+        return self.ctx.lib.dlq_resnet18_launches_for_batch(self.h, n)
+
+    def enable_stamps(self, ring_forwards: int):
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_enable_stamps(self.h, ring_forwards))
+        self._stamp_ring = ring_forwards
+
+    def read_stamps(self) -> np.ndarray:
+        """uint64 [forwards_recorded, launches, 2] = (first block entry, last block exit) in globaltimer ns"""
+        out = np.zeros((self._stamp_ring, self.launches, 2), dtype=np.uint64)
+        n = C.c_int()
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_read_stamps(self.h, out.ctypes.data, C.byref(n)))
+        return out[:n.value]
 
     def forward_host(self, x_host, logits_host):
         """x_host / logits_host: CPU torch tensors (pinned for full speed) or numpy arrays."""
@@ -472,6 +615,7 @@ class ResNet18:
 
     def forward_u8(self, x_hwc, logits):
         """x_hwc: uint8 [N,224,224,3] device tensor (RGB); needs set_preprocess() first"""
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_u8(self.h, _ptr(x_hwc), x_hwc.shape[0], _ptr(logits)))
 
     def forward_host_u8(self, x_hwc_host, logits_host):
@@ -480,10 +624,12 @@ class ResNet18:
         self.ctx._ck(self.ctx.lib.dlq_resnet18_forward_host_u8(self.h, xp, x_hwc_host.shape[0], lp))
 
     def checkpoint(self, name: str, out):
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_checkpoint(self.h, name.encode(), _ptr(out)))
 
     def graph_capture(self, x, logits):
         """capture forward(x, logits) into a CUDA graph (x / logits must stay allocated); replay with graph_launch()"""
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_graph_capture(self.h, _ptr(x), x.shape[0], _ptr(logits)))
 
     def graph_launch(self):
@@ -503,6 +649,7 @@ class ResNet18:
     def profile(self, x, logits) -> np.ndarray:
         """per-launch device milliseconds of one forward (CUDA events on the context stream)"""
         ms = np.zeros(self.launches, dtype=np.float32)
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_profile(self.h, _ptr(x), x.shape[0], _ptr(logits), ms.ctypes.data))
         return ms
 
@@ -531,9 +678,11 @@ class ResNet18F32:
         self.max_batch = max_batch
 
     def forward(self, x, logits):
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_forward(self.h, _ptr(x), x.shape[0], _ptr(logits)))
 
     def checkpoint(self, name: str, out):
+        self.ctx.order_after_torch()
         self.ctx._ck(self.ctx.lib.dlq_resnet18_f32_checkpoint(self.h, name.encode(), _ptr(out)))
 
     def absmax(self) -> np.ndarray:
@@ -608,26 +757,96 @@ def save_weight_dir(path: str, weights: Dict[str, np.ndarray], act_scale=None):
 
 
 class MultiGPU:
-    """Batch-sharded driver over several devices of one box (host buffers in, host logits out)."""
+    """Batch-sharded driver over several devices of one box (persistent worker thread per device).  The same device
+    may be listed more than once (independent replicas)."""
 
-    def __init__(self, devices, weights: Dict[str, np.ndarray], act_scale, max_batch_per_device: int):
+    def __init__(self, devices, weights: Dict[str, np.ndarray], act_scale, max_batch_per_device: int, fp8: bool = False):
         self.lib = load_library()
-        s, keep = _weights_struct(weights, act_scale)
+        s, keep = _weights_struct(weights, act_scale, fp8)
         devs = (C.c_int * len(devices))(*devices)
         h = C.c_void_p()
         rc = self.lib.dlq_multi_create(devs, len(devices), C.byref(s), max_batch_per_device, C.byref(h))
         if rc != 0:
             raise DlqError(rc, "dlq_multi_create failed")
         self.h = h
+        self.n_devices = self.lib.dlq_multi_n_devices(h)
 
-    def forward_host(self, x_host, logits_host):
-        xp = x_host.data_ptr() if hasattr(x_host, "data_ptr") else x_host.ctypes.data
-        lp = logits_host.data_ptr() if hasattr(logits_host, "data_ptr") else logits_host.ctypes.data
-        rc = self.lib.dlq_multi_forward_host(self.h, xp, x_host.shape[0], lp)
+    @staticmethod
+    def _hp(t):
+        return t.data_ptr() if hasattr(t, "data_ptr") else t.ctypes.data
+
+    def _ck(self, rc):
         if rc != 0:
             raise DlqError(rc, self.lib.dlq_multi_last_error_string(self.h).decode())
+
+    def set_preprocess(self, mean=ResNet18.IMAGENET_MEAN, std=ResNet18.IMAGENET_STD):
+        mean, std = np.asarray(mean, dtype=np.float32), np.asarray(std, dtype=np.float32)
+        self._ck(self.lib.dlq_multi_set_preprocess(self.h, mean.ctypes.data, std.ctypes.data))
+
+    def forward_host(self, x_host, logits_host):
+        self._ck(self.lib.dlq_multi_forward_host(self.h, self._hp(x_host), x_host.shape[0], self._hp(logits_host)))
+
+    def forward_host_u8(self, x_host, logits_host):
+        self._ck(self.lib.dlq_multi_forward_host_u8(self.h, self._hp(x_host), x_host.shape[0], self._hp(logits_host)))
+
+    def submit_host(self, x_host, logits_host):
+        self._ck(self.lib.dlq_multi_submit_host(self.h, self._hp(x_host), x_host.shape[0], self._hp(logits_host)))
+
+    def submit_host_u8(self, x_host, logits_host):
+        self._ck(self.lib.dlq_multi_submit_host_u8(self.h, self._hp(x_host), x_host.shape[0], self._hp(logits_host)))
+
+    def wait(self):
+        self._ck(self.lib.dlq_multi_wait(self.h))
+
+    def forward_device(self, xs, logits):
+        """xs / logits: lists of device tensors, one per listed device (fp32 [n_g,3,224,224] / [n_g,1000])"""
+        import torch
+        for t in xs:
+            torch.cuda.current_stream(t.device).synchronize()
+        g = self.n_devices
+        xp = (C.c_void_p * g)(*[t.data_ptr() for t in xs])
+        lp = (C.c_void_p * g)(*[t.data_ptr() for t in logits])
+        nn = (C.c_int * g)(*[int(t.shape[0]) for t in xs])
+        self._ck(self.lib.dlq_multi_forward_device(self.h, xp, nn, lp))
 
     def close(self):
         if self.h:
             self.lib.dlq_multi_destroy(self.h)
+            self.h = None
+
+
+class MLP:
+    """Two-layer MLP forward behind the C ABI (dlq_mlp_*): the GPU counterpart of the reference's MNIST forward
+    (CUDA/MNIST_on_GPU/v4.cu:255-302, v5.cu:127-157, v3.c:177-215) on the tensor-core FC core.  w1 [in, hid] and
+    w2 [hid, out] are in the reference's layout."""
+
+    def __init__(self, ctx: Context, w1, b1, w2, b2, s_x: float, s_h: float, max_batch: int, fp8: bool = False):
+        self.ctx = ctx
+        w1 = np.ascontiguousarray(w1, dtype=np.float32)
+        w2 = np.ascontiguousarray(w2, dtype=np.float32)
+        b1 = np.ascontiguousarray(b1, dtype=np.float32)
+        b2 = np.ascontiguousarray(b2, dtype=np.float32)
+        self.n_in, self.n_hid = w1.shape
+        self.n_out = w2.shape[1]
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.dlq_mlp_create(ctx.h, w1.ctypes.data, b1.ctypes.data, w2.ctypes.data, b2.ctypes.data, self.n_in,
+                                       self.n_hid, self.n_out, float(s_x), float(s_h), max_batch, 1 if fp8 else 0, C.byref(h)))
+        self.h = h
+
+    def forward(self, x, logits=None, probs=None):
+        self.ctx.order_after_torch()
+        self.ctx._ck(self.ctx.lib.dlq_mlp_forward(self.h, _ptr(x), x.shape[0], _ptr(logits), _ptr(probs)))
+
+    def checkpoint(self, name: str, out):
+        self.ctx.order_after_torch()
+        self.ctx._ck(self.ctx.lib.dlq_mlp_checkpoint(self.h, name.encode(), _ptr(out)))
+
+    def weight_scales(self, layer: int) -> np.ndarray:
+        s = np.zeros(self.n_hid if layer == 1 else self.n_out, dtype=np.float32)
+        self.ctx._ck(self.ctx.lib.dlq_mlp_weight_scales(self.h, layer, s.ctypes.data))
+        return s
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.dlq_mlp_destroy(self.h)
             self.h = None

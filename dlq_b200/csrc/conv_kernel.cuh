@@ -117,6 +117,10 @@ struct ConvKernelParams {
   int out_planes;         // 1: out is stored as four parity planes (see Act::planes); out_rows_half = total rows / 2
   int out_rows_half;
   int32_t* acc_out;       // optional dense NHWC int32 [N,Ho,Wo,OC] raw accumulators (debug / parity)
+  int acc_f32;            // 1: acc_out receives fp32 t = fmaf(acc, alpha[oc], beta[oc]) (ReLU if `relu`) instead of the raw
+                          // accumulators: the FC / logits form, R/infer_e2e.cu:206-219 (bias after the product)
+  unsigned long long* stamps;   // optional [2]: min globaltimer at CTA entry, max at CTA exit (ns) - the launch's span inside
+                                // a running step (bench.py roofline); one atomic per CTA at each end
   // Fused second conv (ResNet downsample blocks, R/infer_e2e.cu:181-196): the 1x1/s2 shortcut conv reads exactly the
   // A view of the 3x3/s2 conv's centre tap, so both run from ONE patch load: steps flagged kStepSecond multiply that
   // view with the shortcut's weights into a second accumulator block (TMEM columns + MT*n_tile), and the epilogue
@@ -237,10 +241,12 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
         }
         if (c.leader) {
           const uint32_t b_lo = b_flags + (RESIDENT ? static_cast<uint32_t>(k) : bs) * c.b_stage16;
-          // K-split: the second issuer only accumulates, and only after the first one has issued the overwriting MMA
-          if (KSEL == 2) mbar_wait(&c.k_first[cs], cph);
+          // K-split: the second issuer only accumulates, and only after the first one's overwriting MMA has
+          // COMPLETED: tcgen05 orders the MMAs of one thread only, so the hand-off is a tcgen05.commit on k_first
+          // (arrives when the first issuer's MMAs so far are done) plus tcgen05.fence::after_thread_sync here
+          if (KSEL == 2) { mbar_wait(&c.k_first[cs], cph); tc_fence_after(); }
           if (!(dbg_flags(c.dbg) & 2)) issue_step<ROWB, MYMT, KSEL != 2, TWO, KSEL, FP8>(a_hi, b_hi, a_base + c.step_a16[k], b_lo, d0, c.n_tile, idesc);
-          if (KSEL == 1) mbar_arrive(&c.k_first[cs]);
+          if (KSEL == 1) umma_done<TWO>(&c.k_first[cs]);
           if (!RESIDENT) umma_done<TWO>(&c.b_empty[bs]);
         }
         if (!RESIDENT) { if (++bs == static_cast<uint32_t>(c.b_stages)) { bs = 0; bph ^= 1u; } }
@@ -418,14 +424,31 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
       __syncwarp();
       if (e.lane == 0) mbar_arrive_cluster(acc_empty_addr);     // (rank-0 CTA's barrier when running as a pair)
     }
-    if (ACC_OUT) {                    // raw accumulators (parity / debug entry points only)
+    if (ACC_OUT) {                    // raw accumulators (parity / debug entry points), or the fp32 FC form
 #pragma unroll
       for (int u = 0; u < NU; ++u)
         if (valid[u]) {
           int4* dst = reinterpret_cast<int4*>(p.acc_out + dpix[u] * p.OC + e.n0 + c0[u] + h * 32);
+          if (p.acc_f32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_int4((int)v[u][4 * j], (int)v[u][4 * j + 1], (int)v[u][4 * j + 2], (int)v[u][4 * j + 3]);
+            for (int j = 0; j < 8; ++j) {
+              const float4 al = reinterpret_cast<const float4*>(e.s_alpha + c0[u] + h * 32)[j];
+              const float4 be = reinterpret_cast<const float4*>(e.s_beta + c0[u] + h * 32)[j];
+              float t[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float a = FP8 ? __uint_as_float(v[u][4 * j + i]) : static_cast<float>(static_cast<int32_t>(v[u][4 * j + i]));
+                t[i] = __fmaf_rn(a, i == 0 ? al.x : i == 1 ? al.y : i == 2 ? al.z : al.w,
+                                 i == 0 ? be.x : i == 1 ? be.y : i == 2 ? be.z : be.w);
+                if (e.relu_mask && t[i] < 0.f) t[i] = 0.f;
+              }
+              dst[j] = make_int4(__float_as_int(t[0]), __float_as_int(t[1]), __float_as_int(t[2]), __float_as_int(t[3]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_int4((int)v[u][4 * j], (int)v[u][4 * j + 1], (int)v[u][4 * j + 2], (int)v[u][4 * j + 3]);
+          }
         }
     }
     uint32_t packed[NU][8];
@@ -517,6 +540,11 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   constexpr uint32_t TILE16 = kTileM * ROWB / 16;      // one M tile further down the patch, in 16-byte units
 
   const long long t_entry = dbg_clock();
+  if (p.stamps && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    atomicMin(p.stamps, gt);
+  }
   if (p.dbg_times && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -551,9 +579,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   // Two MMA-issuing warps (1 and 3): a single one cannot keep the tensor pipe fed (the per-step barrier wait and
   // descriptor arithmetic are exposed, probe/mma_rate.cu "pattern").  They split the M tiles of a super-tile when
   // there are at least two, else the K=32 slices of every step (same accumulator; integer accumulation commutes,
-  // the overwriting first MMA is ordered by a handshake).
+  // the overwriting first MMA is ordered by a tcgen05.commit hand-off).  FP32 accumulation does not commute: the
+  // E4M3 instantiation keeps ONE issuer per accumulator, so its results do not depend on timing.
   constexpr int K32 = ROWB / 32;
-  const bool k_split = p.MT == 1 && K32 >= 2;
+  const bool k_split = !FP8 && p.MT == 1 && K32 >= 2;
   const int n_issuers = (p.MT >= 2 || k_split) ? 2 : 1;
   const int ncta = TWO ? 2 : 1;
   const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
@@ -685,6 +714,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8, true>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8, true>(c, tt); }
       } else if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
       else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8>(c, tt); }
+    } else if (p.fused) {     // (one tile per item and no K split: the E4M3 network's fused shortcut, or the 32-byte stem rows)
+      if (p.b_resident) run_issuer<ROWB, 1, true, TWO, 0, FP8, true>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0, FP8, true>(c, tt);
     } else if (p.b_resident) {
       if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0, FP8>(c, tt);
     } else {
@@ -830,6 +861,11 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.dbg_times[static_cast<size_t>(blockIdx.x) * 16 + 13] = static_cast<long long>(gt);     // CTA done, ns
+  }
+  if (p.stamps && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    atomicMax(p.stamps + 1, gt);
   }
   if (TWO) cluster_sync_all();   // nobody leaves while the peer may still arrive on its barriers / read its smem
   if (warp == 1) {

@@ -141,7 +141,7 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
   // 128-channel tiles run as CTA pairs (cta_group::2, M = 256): per SM an MMA then reads 4 KB of A + 2 KB of B per
   // 64 tensor cycles, inside the 128 B/clk shared-memory budget; 64-channel layers stay single-CTA
   out->n_tile = (OC % 128 == 0) ? 128 : 64;
-  if (const char* e = getenv("DLQ_DBG_NTILE")) { const int v = atoi(e); if (v >= 64 && OC % v == 0) out->n_tile = v; }
+  if (const char* e = dlq_dbg_env("DLQ_DBG_NTILE")) { const int v = atoi(e); if (v >= 64 && OC % v == 0) out->n_tile = v; }
   out->fused = 0;
   if (second_wq) {
     DLQ_ARG(ctx, out->kind == CONV_S2_3x3, "a fused 1x1/s2 shortcut needs a 3x3/s2/p1 main conv");
@@ -209,7 +209,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       p.Wo = in.W + 2 * w->pW - w->kW + 1;
       // virtual row pitch: W + pad, not W + 2 pad - the zero column left of row r+1 doubles as the zero column
       // right of row r (the patch is one linear run of pixels), exactly as the pad rows are shared between images
-      p.Wp = in.W + (getenv("DLQ_DBG_WIDE_ROWS") ? 2 * w->pW : w->pW);
+      p.Wp = in.W + (dlq_dbg_env("DLQ_DBG_WIDE_ROWS") ? 2 * w->pW : w->pW);
       if (p.Wp < p.Wo) p.Wp = p.Wo;
       p.Pv = in.H + in.PR;
       break;
@@ -291,8 +291,8 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   // CTAs then view their patches through identical descriptors).  Single CTA: MT tiles per super-tile.
   const int n_tiles = w->OC / w->n_tile;
   p.n_tiles = n_tiles;
-  p.two = (w->n_tile == 128 && p.Wp <= kTileM && !getenv("DLQ_DBG_NO_PAIR")) ? 1 : 0;
-  if (getenv("DLQ_DBG_PAIR64") && w->n_tile == 64 && p.Wp <= 2 * kTileM && (w->kind != CONV_STEM || atoi(getenv("DLQ_DBG_PAIR64")) > 1)) p.two = 1;
+  p.two = (w->n_tile == 128 && p.Wp <= kTileM && !dlq_dbg_env("DLQ_DBG_NO_PAIR")) ? 1 : 0;
+  if (dlq_dbg_env("DLQ_DBG_PAIR64") && w->n_tile == 64 && p.Wp <= 2 * kTileM && (w->kind != CONV_STEM || atoi(dlq_dbg_env("DLQ_DBG_PAIR64")) > 1)) p.two = 1;
   const int ncta = p.two ? 2 : 1;
   p.w_rows = w->n_tile / ncta;
   p.step_bytes = static_cast<uint32_t>(p.w_rows) * rowb;
@@ -301,7 +301,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
   if (w->fused) MT = 1;      // two accumulator blocks per tile: 2 * n_tile columns per stage
-  if (const char* e = getenv("DLQ_DBG_MT")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * p.n_tile <= 512) MT = v; }
+  if (const char* e = dlq_dbg_env("DLQ_DBG_MT")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * p.n_tile <= 512) MT = v; }
   int NR = 0;
   const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;
   for (;; MT >>= 1) {
@@ -316,18 +316,18 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
       p.b_stages = p.n_steps;
     } else {
       const size_t left = budget > static_cast<size_t>(min_a) * p.sub_bytes ? budget - static_cast<size_t>(min_a) * p.sub_bytes : 0;
-      const int b_cap = getenv("DLQ_DBG_B_CAP") ? atoi(getenv("DLQ_DBG_B_CAP")) : 8;     // (tuning)
+      const int b_cap = dlq_dbg_env("DLQ_DBG_B_CAP") ? atoi(dlq_dbg_env("DLQ_DBG_B_CAP")) : 8;     // (tuning)
       p.b_stages = static_cast<int>(std::min<size_t>(std::min(p.n_steps, b_cap), left / b_stage_bytes));
     }
     const size_t b_bytes = static_cast<size_t>(std::max(p.b_stages, 0)) * b_stage_bytes;
-    const int want_a = std::min(getenv("DLQ_DBG_A_CAP") ? atoi(getenv("DLQ_DBG_A_CAP")) : 4, p.n_sub + 2);
+    const int want_a = std::min(dlq_dbg_env("DLQ_DBG_A_CAP") ? atoi(dlq_dbg_env("DLQ_DBG_A_CAP")) : 4, p.n_sub + 2);
     const int fit_a = budget > b_bytes ? static_cast<int>((budget - b_bytes) / p.sub_bytes) : 0;
     p.a_stages = std::min(want_a, fit_a);
     if ((p.a_stages >= 2 && p.b_stages >= std::min(p.n_steps, 3) && es * NR <= 256) || MT == 1) break;
   }
   // debug / tuning overrides (environment; not used by tests or the benchmark)
-  if (const char* e = getenv("DLQ_DBG_A_STAGES")) p.a_stages = atoi(e);
-  if (const char* e = getenv("DLQ_DBG_B_STAGES")) { if (!p.b_resident) p.b_stages = atoi(e); }
+  if (const char* e = dlq_dbg_env("DLQ_DBG_A_STAGES")) p.a_stages = atoi(e);
+  if (const char* e = dlq_dbg_env("DLQ_DBG_B_STAGES")) { if (!p.b_resident) p.b_stages = atoi(e); }
   DLQ_ARG(ctx, p.a_stages >= 1 && p.b_stages >= 1 && es * NR <= 256 && es * p.Wp <= 256 && w->OC <= 2048,
           "conv patch does not fit shared memory / TMA box");
   p.MT = MT;
@@ -367,18 +367,12 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     p.alpha2 = second->alpha; p.beta2 = second->beta; p.relu2 = second->relu;
     p.out2 = second->out.ptr; p.out2_PR = second->out.PR;
   }
-  if (getenv("DLQ_DBG_NO_STORE")) { p.out = nullptr; p.acc_out = nullptr; }
-  if (const char* e = getenv("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
+  if (dlq_dbg_env("DLQ_DBG_NO_STORE")) { p.out = nullptr; p.acc_out = nullptr; }
+  if (const char* e = dlq_dbg_env("DLQ_DBG_FLAGS")) p.dbg = atoi(e);
   // DLQ_DBG_TIMES=1: per-CTA cycle counters (MMA warp: total / wait acc_empty / wait a_full / wait b_full;
   // epilogue warp 0: total / wait acc_full; A producer: total / wait a_empty), printed by launch_conv
-#ifndef DLQ_TIMING
-  if (getenv("DLQ_DBG_TIMES")) {
-    static bool told = false;
-    if (!told) fprintf(stderr, "[dlq] DLQ_DBG_TIMES needs a library built with `make -C dlq_b200/csrc clean && make -C dlq_b200/csrc TIMING=1`\n");
-    told = true;
-  }
-#else
-  if (getenv("DLQ_DBG_TIMES")) {
+#ifdef DLQ_TIMING
+  if (dlq_dbg_env("DLQ_DBG_TIMES")) {
     static long long* buf = nullptr;
     if (!buf) cudaMalloc(&buf, 16 * sizeof(long long) * 1024);
     cudaMemset(buf, 0, 16 * sizeof(long long) * 1024);
@@ -437,12 +431,6 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
 
 template <int ROWB, bool TWO, bool FP8>
 static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
-  static size_t configured[16] = {0};   // per-device max dynamic smem already requested
-  if (configured[ctx->device & 15] < L.smem) {
-    DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(ctx->smem_optin)));
-    configured[ctx->device & 15] = ctx->smem_optin;
-  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = L.grid;
   cfg.blockDim = L.block;
@@ -458,7 +446,7 @@ static int launch_t(dlq_ctx* ctx, const ConvLaunch& L) {
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("DLQ_DBG_NO_PDL") ? 1 : 2;
+  cfg.numAttrs = ctx->no_pdl ? 1 : 2;
   DLQ_CUDA(ctx, cudaLaunchKernelEx(&cfg, conv_i8_kernel<ROWB, TWO, FP8>, L.tmap, L.tmap_w, L.p));
   if (L.p.dbg_times) {
     cudaStreamSynchronize(ctx->stream);
@@ -502,6 +490,29 @@ static int launch_rowb(dlq_ctx* ctx, const ConvLaunch& L) {
   }
   ctx->err = "internal: bad rowb";
   return DLQ_ERR_ARG;
+}
+
+// every instantiation's dynamic shared-memory limit, once per context (= per device): no function-static state, so
+// contexts on different devices / threads are independent (dlq.h), and a cubin that does not load fails dlq_create
+template <int ROWB, bool TWO, bool FP8>
+static cudaError_t configure_t(dlq_ctx* ctx) {
+  return cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              static_cast<int>(ctx->smem_optin));
+}
+int configure_conv_kernels(dlq_ctx* ctx) {
+  DLQ_CUDA(ctx, (configure_t<32, false, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<64, false, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<128, false, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<32, true, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<64, true, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<128, true, false>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<32, false, true>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<64, false, true>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<128, false, true>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<32, true, true>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<64, true, true>(ctx)));
+  DLQ_CUDA(ctx, (configure_t<128, true, true>(ctx)));
+  return DLQ_OK;
 }
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {

@@ -36,11 +36,22 @@ int dlq_create(int device, dlq_ctx** out) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->no_pdl = dlq_dbg_env("DLQ_DBG_NO_PDL") != nullptr;
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return DLQ_ERR_CUDA;
   }
   c->own_stream = true;
+  // kernel attributes once per context; an sm_100a image that does not load on this device (sm_101 / sm_103 report
+  // major 10 too) fails here, loudly, instead of at the first launch
+  if (configure_conv_kernels(c) != DLQ_OK || configure_elementwise_kernels(c) != DLQ_OK ||
+      cudaMalloc(&c->small, 256) != cudaSuccess) {
+    fprintf(stderr, "dlq_b200: device %d (sm_%d%d) cannot run the sm_100a kernels of this library: %s\n", device, prop.major,
+            prop.minor, c->err.c_str());
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return DLQ_ERR_CUDA;
+  }
   *out = c;
   return DLQ_OK;
 }
@@ -49,10 +60,21 @@ void dlq_destroy(dlq_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (int i = 0; i < 4; ++i)
-    if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->small) cudaFree(ctx->small);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
+}
+
+/* workspace of the per-layer NCHW entry points (SURVEY 8b "Ownership") */
+size_t dlq_workspace_bytes(const dlq_ctx* ctx) { return ctx ? ctx->ws_bytes : 0; }
+int dlq_workspace_reserve(dlq_ctx* ctx, size_t bytes) {
+  if (!ctx) return DLQ_ERR_ARG;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->ws_reserved = false;
+  const int rc = ctx_workspace(ctx, bytes);
+  ctx->ws_reserved = (rc == DLQ_OK);
+  return rc;
 }
 
 const char* dlq_last_error_string(const dlq_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -127,6 +149,9 @@ uint8_t f32_to_e4m3_host(float f) {
   return static_cast<uint8_t>(sign | ((ex + 7) << 3) | m);
 }
 
+}  // namespace
+
+namespace dlq {
 void quantize_rows_e4m3(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s) {
   q.resize(static_cast<size_t>(rows) * K);
   s.resize(rows);
@@ -154,7 +179,7 @@ void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std:
   }
 }
 
-}  // namespace
+}  // namespace dlq
 
 extern "C" {
 void dlq_fold_bn(const float* g, const float* b, const float* m, const float* v, float eps, const float* s_w,
@@ -256,6 +281,40 @@ int dlq_conv2d_fp8(dlq_ctx* ctx, const uint8_t* x, int N, int C, int H, int W, c
                       reinterpret_cast<int32_t*>(acc_out), OH, OW);
 }
 
+// geometry of the four workspace regions dlq_conv2d_* carves (input in the library's layout, output, residual, raw
+// accumulators), each rounded up to 1 KB
+namespace {
+struct ConvWs {
+  Act in, out;
+  size_t off_in = 0, off_out = 0, off_res = 0, off_acc = 0, total = 0;
+};
+inline size_t ws_align(size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); }
+ConvWs conv_ws_layout(const dlq_conv_weights* w, int N, int H, int W, bool want_y, bool has_res, bool want_acc) {
+  ConvWs L;
+  int oh, ow;
+  conv_out_dims(w, H, W, &oh, &ow);
+  L.in.N = N; L.in.PR = conv_required_in_pr(w);
+  if (w->kind == CONV_STEM) { L.in.H = H / 2; L.in.W = W / 2 + 3; L.in.C = 32; }
+  else { L.in.H = H; L.in.W = W; L.in.C = w->IC; }
+  L.out.N = N; L.out.H = oh; L.out.W = ow; L.out.C = w->OC; L.out.PR = 0;
+  size_t off = 0;
+  L.off_in = off; off += ws_align(L.in.bytes() + 1024);
+  L.off_out = off; if (want_y) off += ws_align(L.out.bytes());
+  L.off_res = off; if (has_res) off += ws_align(L.out.bytes());
+  L.off_acc = off; if (want_acc) off += ws_align(static_cast<size_t>(N) * oh * ow * w->OC * 4);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+/* bytes of workspace dlq_conv2d_i8 / dlq_conv2d_fp8 need for this call shape: pass the maximum over the calls you will
+ * make to dlq_workspace_reserve() once and the per-layer entry points never allocate (they grow the workspace on demand,
+ * with a synchronisation, only when nothing was reserved) */
+size_t dlq_conv2d_workspace_bytes(const dlq_conv_weights* w, int N, int H, int W, int has_residual, int want_acc) {
+  if (!w || N <= 0 || H <= 0 || W <= 0) return 0;
+  return conv_ws_layout(w, N, H, W, true, has_residual != 0, want_acc != 0).total;
+}
+
 static int conv2d_bytes(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
                        const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW) {
   if (!ctx) return DLQ_ERR_ARG;
@@ -270,38 +329,25 @@ static int conv2d_bytes(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int 
   if (OW) *OW = ow;
   if (N == 0) return DLQ_OK;
   DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (w->kind == CONV_STEM) DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
 
-  Act in, out, res;
-  in.N = N; in.PR = conv_required_in_pr(w);
-  if (w->kind == CONV_STEM) {
-    DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0, "stem needs even H, W");
-    in.H = H / 2; in.W = W / 2 + 3; in.C = 32;
-  } else {
-    in.H = H; in.W = W; in.C = C;
-  }
-  out.N = N; out.H = oh; out.W = ow; out.C = w->OC; out.PR = 0;
-  res = out;
-  in.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 0, in.bytes()));
-  DLQ_ARG(ctx, in.ptr != nullptr, "out of device memory (scratch)");
-  DLQ_CUDA(ctx, cudaMemsetAsync(in.ptr, 0, in.bytes(), ctx->stream));
-  int rc = (w->kind == CONV_STEM) ? nchw_i8_to_stem_s2d(ctx, x, N, H, W, in) : nchw_to_act_i8(ctx, x, in);
-  if (rc != DLQ_OK) return rc;
-  if (y) {
-    out.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 1, out.bytes()));
-    DLQ_ARG(ctx, out.ptr != nullptr, "out of device memory (scratch)");
-  }
   const bool has_res = ep && ep->residual;
+  const ConvWs ws = conv_ws_layout(w, N, H, W, y != nullptr, has_res, acc_out != nullptr);
+  int rc = ctx_workspace(ctx, ws.total);        // no allocation once the workspace is large enough / reserved
+  if (rc != DLQ_OK) return rc;
+  uint8_t* base = static_cast<uint8_t*>(ctx->ws);
+  Act in = ws.in, out = ws.out, res = ws.out;
+  in.ptr = reinterpret_cast<int8_t*>(base + ws.off_in);
+  DLQ_CUDA(ctx, cudaMemsetAsync(in.ptr, 0, in.bytes() + 1024, ctx->stream));
+  rc = (w->kind == CONV_STEM) ? nchw_i8_to_stem_s2d(ctx, x, N, H, W, in) : nchw_to_act_i8(ctx, x, in);
+  if (rc != DLQ_OK) return rc;
+  if (y) out.ptr = reinterpret_cast<int8_t*>(base + ws.off_out);
   if (has_res) {
-    res.ptr = static_cast<int8_t*>(ctx_scratch(ctx, 2, res.bytes()));
-    DLQ_ARG(ctx, res.ptr != nullptr, "out of device memory (scratch)");
+    res.ptr = reinterpret_cast<int8_t*>(base + ws.off_res);
     rc = nchw_to_act_i8(ctx, ep->residual, res);
     if (rc != DLQ_OK) return rc;
   }
-  int32_t* acc_nhwc = nullptr;
-  if (acc_out) {
-    acc_nhwc = static_cast<int32_t*>(ctx_scratch(ctx, 3, static_cast<size_t>(N) * oh * ow * w->OC * 4));
-    DLQ_ARG(ctx, acc_nhwc != nullptr, "out of device memory (scratch)");
-  }
+  int32_t* acc_nhwc = acc_out ? reinterpret_cast<int32_t*>(base + ws.off_acc) : nullptr;
   ConvLaunch L;
   rc = plan_conv(ctx, w, in, out, ep ? ep->alpha : nullptr, ep ? ep->beta : nullptr, has_res ? &res : nullptr,
                  ep ? ep->res_mul : 0.f, ep ? ep->relu : 0, acc_nhwc, &L);
@@ -425,9 +471,24 @@ struct dlq_resnet18 {
   std::vector<void*> allocs;
   dlq_conv_weights* conv_fused[8] = {nullptr};   // downsample blocks: conv1 + shortcut in one weight image (small batches)
   uint8_t* d_lut = nullptr;   // [3][256] uint8 pixel value -> quantised stem input (dlq_resnet18_set_preprocess)
-  uint8_t* d_xu8 = nullptr;   // staging for forward_host_u8
-  float* d_x = nullptr;       // staging for forward_host
-  float* d_logits = nullptr;
+  // Host-buffer entry points: two staging slots (input + logits), allocated on first use, so that the H2D copy of
+  // call k+1 overlaps the forward of call k and the D2H copy of call k-1 (dlq_resnet18_submit_host* / _wait).
+  struct HostSlot {
+    void* d_in = nullptr;       // fp32 NCHW or uint8 HWC batch
+    size_t in_bytes = 0;
+    float* d_logits = nullptr;
+    cudaEvent_t h2d_done = nullptr, compute_done = nullptr, d2h_done = nullptr;
+    bool busy = false;
+  };
+  HostSlot slot[2];
+  int next_slot = 0;
+  int fifo[2] = {0, 0};       // outstanding submits, oldest first
+  int n_outstanding = 0;
+  cudaStream_t d2h_stream = nullptr;
+  // span stamps: ring of [forward][launch][2] globaltimer values (dlq_resnet18_enable_stamps)
+  unsigned long long* d_stamps = nullptr;
+  int stamp_ring = 0;
+  unsigned long long fwd_count = 0;
   struct Plan {
     int N = 0;
     ConvLaunch L[DLQ_NUM_CONVS];
@@ -439,7 +500,6 @@ struct dlq_resnet18 {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t copy_stream = nullptr;   // forward_host pipelining
   cudaEvent_t copy_done[64] = {nullptr};
-  cudaEvent_t compute_done = nullptr;
 };
 
 namespace {
@@ -497,7 +557,7 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
     // Fusing the shortcut into conv1 saves a launch and a second pass over the input, but forces one tile per
     // item (two accumulator blocks per tile in TMEM): it wins at small batches (latency), loses at large ones.
-    const int fuse_max = getenv("DLQ_DBG_FUSE_MAX") ? atoi(getenv("DLQ_DBG_FUSE_MAX")) : kFuseMaxBatch;   // (tuning)
+    const int fuse_max = dlq_dbg_env("DLQ_DBG_FUSE_MAX") ? atoi(dlq_dbg_env("DLQ_DBG_FUSE_MAX")) : kFuseMaxBatch;   // (tuning)
     P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= fuse_max;
     if (P->fused[b]) {
       SecondConv sc;
@@ -540,10 +600,22 @@ void dlq_resnet18_destroy(dlq_resnet18* m) {
   for (void* p : m->allocs) cudaFree(p);
   for (auto& c : m->conv) dlq_conv_weights_free(c);
   if (m->copy_stream) {
+    cudaStreamSynchronize(m->copy_stream);
     cudaStreamDestroy(m->copy_stream);
     for (auto& e : m->copy_done) if (e) cudaEventDestroy(e);
-    if (m->compute_done) cudaEventDestroy(m->compute_done);
   }
+  if (m->d2h_stream) {
+    cudaStreamSynchronize(m->d2h_stream);
+    cudaStreamDestroy(m->d2h_stream);
+  }
+  for (auto& sl : m->slot) {
+    if (sl.d_in) cudaFree(sl.d_in);
+    if (sl.d_logits) cudaFree(sl.d_logits);
+    if (sl.h2d_done) cudaEventDestroy(sl.h2d_done);
+    if (sl.compute_done) cudaEventDestroy(sl.compute_done);
+    if (sl.d2h_done) cudaEventDestroy(sl.d2h_done);
+  }
+  if (m->d_stamps) cudaFree(m->d_stamps);
   delete m;
 }
 
@@ -561,7 +633,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   m->max_batch = max_batch;
   std::copy(w->act_scale, w->act_scale + DLQ_NUM_ACTS, m->act_scale);
   m->fp8 = w->fp8 ? 1 : 0;
-  m->fuse_ds = getenv("DLQ_NO_FUSE_DS") == nullptr;
+  m->fuse_ds = dlq_dbg_env("DLQ_NO_FUSE_DS") == nullptr;
 
   // ---- convs: geometry as wired by runtime/infer_e2e.cu:258-407
   struct CG { int ic, oc, k, s, p; float s_in, s_out; };
@@ -644,7 +716,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     if (rc == DLQ_OK && B.down) rc = alloc_act(m.get(), m->a_ds[b], N, hw, hw, B.oc, 0);
     if (rc == DLQ_OK) rc = alloc_act(m.get(), m->a_out[b], N, hw, hw, B.oc, feeds_s2 ? 2 : 1);
     // a block output that only the next block's stride-2 convs read is kept as four parity planes
-    if (rc == DLQ_OK && feeds_s2 && !getenv("DLQ_NO_PLANES")) {
+    if (rc == DLQ_OK && feeds_s2 && !dlq_dbg_env("DLQ_NO_PLANES")) {
       m->a_out[b].planes = 1;
       m->a_out[b].plane_rows = m->a_out[b].rows() / 2;
     }
@@ -655,15 +727,7 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 512));
     m->allocs.push_back(p);
     m->d_gap_q = static_cast<int8_t*>(p);
-    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 3 * 224 * 224 * sizeof(float)));
-    m->allocs.push_back(p);
-    m->d_x = static_cast<float*>(p);
-    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 1000 * sizeof(float)));
-    m->allocs.push_back(p);
-    m->d_logits = static_cast<float*>(p);
-    DLQ_CUDA(ctx, cudaMalloc(&p, static_cast<size_t>(N) * 3 * 224 * 224));
-    m->allocs.push_back(p);
-    m->d_xu8 = static_cast<uint8_t*>(p);
+    // (the staging buffers of the host-buffer entry points are allocated on their first use)
     DLQ_CUDA(ctx, cudaMalloc(&p, 768));
     m->allocs.push_back(p);
     m->d_lut = static_cast<uint8_t*>(p);
@@ -678,9 +742,19 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   return DLQ_OK;
 }
 
+/* profile slots of one forward (an upper bound of the launches: at batches <= 16 the three shortcut convs run inside
+ * conv1's launch and their slots stay 0) */
 int dlq_resnet18_launches(const dlq_resnet18* m) {
   (void)m;
   return 1 /*quantise+s2d*/ + 20 /*convs*/ + 1 /*max-pool*/ + 1 /*GAP+FC*/;
+}
+/* kernels one forward of batch N really launches: 23, or 20 when the shortcut convs are fused into conv1 (N <= 16) */
+int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
+  if (!m || N <= 0) return 0;
+  int fused = 0;
+  for (int b = 0; b < 8; ++b)
+    if (kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= kFuseMaxBatch) ++fused;
+  return 23 - fused;
 }
 
 // x: fp32 NCHW input, or (x == nullptr) x_u8: uint8 HWC images mapped through m->d_lut
@@ -704,30 +778,45 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
     if (ev) DLQ_CUDA(ctx, cudaEventRecord(ev[e++], ctx->stream));
     return DLQ_OK;
   };
+  // span stamps (off unless dlq_resnet18_enable_stamps was called): slot i of this forward's ring entry
+  unsigned long long* st_base =
+      m->d_stamps ? m->d_stamps + static_cast<size_t>(m->fwd_count % static_cast<unsigned long long>(m->stamp_ring)) * 23 * 2 : nullptr;
+  ++m->fwd_count;
+  int slot = 0;
+  auto stamp = [&]() -> unsigned long long* { unsigned long long* r = st_base ? st_base + 2 * slot : nullptr; ++slot; return r; };
+  auto conv = [&](const ConvLaunch& L0) -> int {
+    unsigned long long* sp = stamp();
+    if (!sp) return launch_conv(ctx, L0);
+    ConvLaunch L = L0;
+    L.p.stamps = sp;
+    return launch_conv(ctx, L);
+  };
   int rc = mark();
   if (rc != DLQ_OK) return rc;
-  rc = x ? quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N), m->fp8)
-         : preprocess_u8_s2d(ctx, x_u8, N, 224, 224, m->d_lut, with_n(m->a_in, N));
+  rc = x ? quantize_input_s2d(ctx, x, N, 224, 224, inv_scale(S[kActInput]), with_n(m->a_in, N), m->fp8, stamp())
+         : preprocess_u8_s2d(ctx, x_u8, N, 224, 224, m->d_lut, with_n(m->a_in, N), stamp());
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
-  rc = launch_conv(ctx, P.L[0]);
+  rc = conv(P.L[0]);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
-  rc = maxpool_act(ctx, with_n(m->a_stem, N), with_n(m->a_pool, N));
+  rc = maxpool_act(ctx, with_n(m->a_stem, N), with_n(m->a_pool, N), stamp());
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   for (int b = 0; b < 8; ++b) {
-    rc = launch_conv(ctx, P.L[1 + 3 * b]);
+    rc = conv(P.L[1 + 3 * b]);
     if (rc != DLQ_OK) return rc;
     if ((rc = mark()) != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       if (!P.fused[b]) {          // (fused: the shortcut conv ran inside conv1's launch; its profile entry stays 0)
-        rc = launch_conv(ctx, P.L[3 + 3 * b]);
+        rc = conv(P.L[3 + 3 * b]);
         if (rc != DLQ_OK) return rc;
+      } else {
+        (void)stamp();
       }
       if ((rc = mark()) != DLQ_OK) return rc;
     }
-    rc = launch_conv(ctx, P.L[2 + 3 * b]);
+    rc = conv(P.L[2 + 3 * b]);
     if (rc != DLQ_OK) return rc;
     if ((rc = mark()) != DLQ_OK) return rc;
   }
@@ -736,7 +825,7 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   rc = m->fp8 ? gap_fc_act_e4m3(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000,
                                 m->d_gap_q, logits)
               : gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
-                           logits);
+                           logits, stamp());
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   m->last_N = N;
@@ -746,6 +835,48 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
 int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) {
   if (!m) return DLQ_ERR_ARG;
   return forward_impl(m, x, N, logits, nullptr);
+}
+
+/* Span stamps: with a ring of `ring_forwards` entries enabled, every kernel of a forward records the globaltimer (ns) of
+ * its first block entry and last block exit into entry (forward index mod ring) - the launch's span INSIDE a running
+ * sequence of forwards, programmatic-dependent-launch overlap included (what a CUDA event between launches cannot
+ * see).  One atomic per block at each end; ring_forwards = 0 switches them off.  dlq_resnet18_read_stamps synchronises,
+ * copies the ring to HOST memory [ring][dlq_resnet18_launches()][2] (entry, exit; entry == UINT64_MAX: slot not
+ * written) and resets it.  Measurement only (bench.py roofline); the reference brackets each launch with its cudaEvent
+ * Timer instead (R/utils.hpp:85-92). */
+static int reset_stamps(dlq_resnet18* m) {
+  dlq_ctx* ctx = m->ctx;
+  std::vector<unsigned long long> init(static_cast<size_t>(m->stamp_ring) * 23 * 2);
+  for (size_t i = 0; i < init.size(); i += 2) { init[i] = ~0ULL; init[i + 1] = 0ULL; }
+  DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_stamps, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                                ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->fwd_count = 0;
+  return DLQ_OK;
+}
+int dlq_resnet18_enable_stamps(dlq_resnet18* m, int ring_forwards) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, ring_forwards >= 0 && ring_forwards <= 4096, "ring size outside [0, 4096]");
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (m->d_stamps) { cudaFree(m->d_stamps); m->d_stamps = nullptr; }
+  m->stamp_ring = ring_forwards;
+  if (ring_forwards == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaMalloc(&m->d_stamps, static_cast<size_t>(ring_forwards) * 23 * 2 * sizeof(unsigned long long)));
+  return reset_stamps(m);
+}
+int dlq_resnet18_read_stamps(dlq_resnet18* m, unsigned long long* out_host, int* forwards_recorded) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, m->d_stamps && out_host, "stamps are not enabled (dlq_resnet18_enable_stamps) or null pointer");
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DLQ_CUDA(ctx, cudaMemcpy(out_host, m->d_stamps, static_cast<size_t>(m->stamp_ring) * 23 * 2 * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost));
+  if (forwards_recorded)
+    *forwards_recorded = static_cast<int>(std::min<unsigned long long>(m->fwd_count, static_cast<unsigned long long>(m->stamp_ring)));
+  return reset_stamps(m);
 }
 
 // One forward with a CUDA event between consecutive launches (on the context's stream).
@@ -771,7 +902,7 @@ int dlq_resnet18_profile(dlq_resnet18* m, const float* x, int N, float* logits, 
 int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* logits) {
   if (!m) return DLQ_ERR_ARG;
   dlq_ctx* ctx = m->ctx;
-  // a plain forward first: builds the launch plans and sets the kernels' shared-memory attributes outside the capture
+  // a plain forward first: builds the launch plans outside the capture
   int rc = forward_impl(m, x, N, logits, nullptr);
   if (rc != DLQ_OK) return rc;
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -780,9 +911,19 @@ int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* lo
   DLQ_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
   rc = forward_impl(m, x, N, logits, nullptr);
   const cudaError_t e = cudaStreamEndCapture(ctx->stream, &m->graph);
-  if (rc != DLQ_OK) return rc;
-  DLQ_CUDA(ctx, e);
-  DLQ_CUDA(ctx, cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+  if (rc != DLQ_OK || e != cudaSuccess) {          // a failed capture leaves no half-built graph behind
+    if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
+    cudaGetLastError();
+    if (rc != DLQ_OK) return rc;
+    DLQ_CUDA(ctx, e);
+  }
+  const cudaError_t ei = cudaGraphInstantiate(&m->graph_exec, m->graph, 0);
+  if (ei != cudaSuccess) {
+    cudaGraphDestroy(m->graph);
+    m->graph = nullptr;
+    m->graph_exec = nullptr;
+    DLQ_CUDA(ctx, ei);
+  }
   return DLQ_OK;
 }
 
@@ -794,44 +935,160 @@ int dlq_resnet18_graph_launch(dlq_resnet18* m) {
   return DLQ_OK;
 }
 
-int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {
-  if (!m) return DLQ_ERR_ARG;
+// ------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t kImgElems = static_cast<size_t>(3) * 224 * 224;
+
+int host_streams(dlq_resnet18* m) {
   dlq_ctx* ctx = m->ctx;
-  DLQ_ARG(ctx, x_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
-  if (N == 0) return DLQ_OK;
-  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t img = static_cast<size_t>(3) * 224 * 224;
-  // Large batches are pipelined: the H2D copy of chunk k+1 (copy stream) overlaps the forward of chunk k
-  // (compute stream).  The fp32 input is 602 KB/image, so the host link, not the GPU, bounds this entry point.
-  const int chunk = (N >= 128) ? 64 : N;
   if (!m->copy_stream) {
     DLQ_CUDA(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    DLQ_CUDA(ctx, cudaStreamCreateWithFlags(&m->d2h_stream, cudaStreamNonBlocking));
     for (auto& e : m->copy_done) DLQ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    DLQ_CUDA(ctx, cudaEventCreateWithFlags(&m->compute_done, cudaEventDisableTiming));
+    for (auto& sl : m->slot) {
+      DLQ_CUDA(ctx, cudaEventCreateWithFlags(&sl.h2d_done, cudaEventDisableTiming));
+      DLQ_CUDA(ctx, cudaEventCreateWithFlags(&sl.compute_done, cudaEventDisableTiming));
+      DLQ_CUDA(ctx, cudaEventCreateWithFlags(&sl.d2h_done, cudaEventDisableTiming));
+    }
   }
-  // the copy stream must not overwrite d_x while a previous call's compute still reads it
-  DLQ_CUDA(ctx, cudaEventRecord(m->compute_done, ctx->stream));
-  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->compute_done, 0));
+  return DLQ_OK;
+}
+// staging of one slot, grown to `in_bytes` (first use; never on the steady-state path)
+int slot_buffers(dlq_resnet18* m, dlq_resnet18::HostSlot& sl, size_t in_bytes) {
+  dlq_ctx* ctx = m->ctx;
+  if (sl.in_bytes < in_bytes) {
+    if (sl.d_in) { DLQ_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(sl.d_in); sl.d_in = nullptr; sl.in_bytes = 0; }
+    DLQ_CUDA(ctx, cudaMalloc(&sl.d_in, in_bytes));
+    sl.in_bytes = in_bytes;
+  }
+  if (!sl.d_logits) DLQ_CUDA(ctx, cudaMalloc(&sl.d_logits, static_cast<size_t>(m->max_batch) * 1000 * sizeof(float)));
+  return DLQ_OK;
+}
+int wait_oldest(dlq_resnet18* m) {
+  dlq_ctx* ctx = m->ctx;
+  if (m->n_outstanding == 0) return DLQ_OK;
+  dlq_resnet18::HostSlot& sl = m->slot[m->fifo[0]];
+  DLQ_CUDA(ctx, cudaEventSynchronize(sl.d2h_done));
+  sl.busy = false;
+  m->fifo[0] = m->fifo[1];
+  --m->n_outstanding;
+  return DLQ_OK;
+}
+
+// Enqueue one whole-batch forward from host memory into slot staging: H2D on the copy stream (after the slot's previous
+// forward has consumed its input), forward on the compute stream, D2H of the logits on a third stream.  Returns
+// without synchronising unless both slots are in flight (then it first waits for the older one).
+int submit_host(dlq_resnet18* m, const void* x_host, int N, float* logits_host, bool u8) {
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, x_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  DLQ_ARG(ctx, !u8 || m->has_lut, "call dlq_resnet18_set_preprocess first");
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = host_streams(m);
+  if (rc != DLQ_OK) return rc;
+  if (m->n_outstanding == 2 && (rc = wait_oldest(m)) != DLQ_OK) return rc;
+  const int si = m->next_slot;
+  dlq_resnet18::HostSlot& sl = m->slot[si];
+  const size_t elem = u8 ? 1 : sizeof(float);
+  rc = slot_buffers(m, sl, static_cast<size_t>(m->max_batch) * kImgElems * elem);
+  if (rc != DLQ_OK) return rc;
+  // H2D: the slot's previous forward (two submits ago) must have read its input
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, sl.compute_done, 0));
+  DLQ_CUDA(ctx, cudaMemcpyAsync(sl.d_in, x_host, static_cast<size_t>(N) * kImgElems * elem, cudaMemcpyHostToDevice, m->copy_stream));
+  DLQ_CUDA(ctx, cudaEventRecord(sl.h2d_done, m->copy_stream));
+  // forward: after its input has landed and the slot's previous logits have left the device
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.h2d_done, 0));
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, sl.d2h_done, 0));
+  rc = u8 ? forward_impl(m, nullptr, N, sl.d_logits, nullptr, static_cast<const uint8_t*>(sl.d_in))
+          : forward_impl(m, static_cast<const float*>(sl.d_in), N, sl.d_logits, nullptr);
+  if (rc != DLQ_OK) return rc;
+  DLQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+  // D2H of the logits
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->d2h_stream, sl.compute_done, 0));
+  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, sl.d_logits, static_cast<size_t>(N) * 1000 * sizeof(float), cudaMemcpyDeviceToHost,
+                                m->d2h_stream));
+  DLQ_CUDA(ctx, cudaEventRecord(sl.d2h_done, m->d2h_stream));
+  sl.busy = true;
+  m->fifo[m->n_outstanding++] = si;
+  m->next_slot ^= 1;
+  return DLQ_OK;
+}
+
+// Synchronous form: within ONE call, large batches are pipelined in chunks (the H2D copy of chunk k+1 overlaps the forward
+// of chunk k); the fp32 input is 602 KB/image, so the host link, not the GPU, bounds this entry point.
+int forward_host_sync(dlq_resnet18* m, const void* x_host, int N, float* logits_host, bool u8) {
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, x_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
+  DLQ_ARG(ctx, !u8 || m->has_lut, "call dlq_resnet18_set_preprocess first");
+  if (N == 0) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  int rc = host_streams(m);
+  if (rc != DLQ_OK) return rc;
+  while (m->n_outstanding) if ((rc = wait_oldest(m)) != DLQ_OK) return rc;     // drain submitted work first
+  const size_t elem = u8 ? 1 : sizeof(float);
+  dlq_resnet18::HostSlot& sl = m->slot[0];
+  rc = slot_buffers(m, sl, static_cast<size_t>(m->max_batch) * kImgElems * elem);
+  if (rc != DLQ_OK) return rc;
+  // chunk size: 64 (fp32) / 128 (uint8: a chunk copies 4x faster) images for N >= 128, never more than 64 chunks
+  const int n_ev = static_cast<int>(sizeof(m->copy_done) / sizeof(m->copy_done[0]));
+  int chunk = N;
+  if (N >= 128) chunk = std::max((u8 && N >= 256) ? 128 : 64, (N + n_ev - 1) / n_ev);
+  // the copy stream must not overwrite the staging buffer while a previous call's compute still reads it
+  DLQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
+  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, sl.compute_done, 0));
+  const uint8_t* src = static_cast<const uint8_t*>(x_host);
+  uint8_t* dst = static_cast<uint8_t*>(sl.d_in);
   int k = 0;
   for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
     const int n = std::min(chunk, N - n0);
-    DLQ_ARG(ctx, k < static_cast<int>(sizeof(m->copy_done) / sizeof(m->copy_done[0])), "too many chunks");
-    DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_x + n0 * img, x_host + n0 * img, n * img * sizeof(float), cudaMemcpyHostToDevice,
-                                  m->copy_stream));
+    DLQ_CUDA(ctx, cudaMemcpyAsync(dst + n0 * kImgElems * elem, src + n0 * kImgElems * elem, n * kImgElems * elem,
+                                  cudaMemcpyHostToDevice, m->copy_stream));
     DLQ_CUDA(ctx, cudaEventRecord(m->copy_done[k], m->copy_stream));
   }
   k = 0;
+  int last_n = N;
   for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
     const int n = std::min(chunk, N - n0);
     DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copy_done[k], 0));
-    const int rc = forward_impl(m, m->d_x + n0 * img, n, m->d_logits + static_cast<size_t>(n0) * 1000, nullptr);
+    float* lg = sl.d_logits + static_cast<size_t>(n0) * 1000;
+    rc = u8 ? forward_impl(m, nullptr, n, lg, nullptr, dst + n0 * kImgElems)
+            : forward_impl(m, reinterpret_cast<const float*>(dst) + n0 * kImgElems, n, lg, nullptr);
     if (rc != DLQ_OK) return rc;
+    last_n = n;
   }
-  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, m->d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
+  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, sl.d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
                                 cudaMemcpyDeviceToHost, ctx->stream));
+  DLQ_CUDA(ctx, cudaEventRecord(sl.compute_done, ctx->stream));
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  m->last_N = std::min(chunk, N - (k - 1) * chunk);   // checkpoints refer to the last chunk
+  m->last_N = last_n;   // checkpoints refer to the last chunk
   return DLQ_OK;
+}
+}  // namespace
+
+int dlq_resnet18_forward_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {
+  if (!m) return DLQ_ERR_ARG;
+  return forward_host_sync(m, x_host, N, logits_host, false);
+}
+
+/* Pipelined form of the host-buffer entry points: submit enqueues H2D -> forward (the WHOLE batch in one pass) -> D2H and
+ * returns; up to two submits may be in flight, so that the copy of batch k+1 overlaps the forward of batch k and the
+ * logits copy of batch k-1.  dlq_resnet18_wait blocks until the OLDEST outstanding submit's logits are in host memory
+ * (returns immediately when nothing is outstanding).  x_host must stay valid until the matching wait; pinned host
+ * memory gives full speed. */
+int dlq_resnet18_submit_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host) {
+  if (!m) return DLQ_ERR_ARG;
+  return submit_host(m, x_host, N, logits_host, false);
+}
+int dlq_resnet18_submit_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int N, float* logits_host) {
+  if (!m) return DLQ_ERR_ARG;
+  return submit_host(m, x_hwc_host, N, logits_host, true);
+}
+int dlq_resnet18_wait(dlq_resnet18* m) {
+  if (!m) return DLQ_ERR_ARG;
+  DLQ_CUDA(m->ctx, cudaSetDevice(m->ctx->device));
+  return wait_oldest(m);
 }
 
 /* uint8 input path.  The reference normalises on the host in Python (tools/preprocess_to_bin.py:24-33:
@@ -870,39 +1127,7 @@ int dlq_resnet18_forward_u8(dlq_resnet18* m, const uint8_t* x_hwc, int N, float*
  * large batches are pipelined in chunks like dlq_resnet18_forward_host */
 int dlq_resnet18_forward_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int N, float* logits_host) {
   if (!m) return DLQ_ERR_ARG;
-  dlq_ctx* ctx = m->ctx;
-  DLQ_ARG(ctx, x_hwc_host && logits_host && N >= 0 && N <= m->max_batch, "null pointer or batch larger than max_batch");
-  DLQ_ARG(ctx, m->has_lut, "call dlq_resnet18_set_preprocess first");
-  if (N == 0) return DLQ_OK;
-  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t img = static_cast<size_t>(3) * 224 * 224;
-  const int chunk = (N >= 256) ? 128 : (N >= 128) ? 64 : N;   // (a uint8 chunk copies 4x faster than an fp32 one)
-  if (!m->copy_stream) {
-    DLQ_CUDA(ctx, cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-    for (auto& e : m->copy_done) DLQ_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    DLQ_CUDA(ctx, cudaEventCreateWithFlags(&m->compute_done, cudaEventDisableTiming));
-  }
-  DLQ_CUDA(ctx, cudaEventRecord(m->compute_done, ctx->stream));
-  DLQ_CUDA(ctx, cudaStreamWaitEvent(m->copy_stream, m->compute_done, 0));
-  int k = 0;
-  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
-    const int n = std::min(chunk, N - n0);
-    DLQ_ARG(ctx, k < static_cast<int>(sizeof(m->copy_done) / sizeof(m->copy_done[0])), "too many chunks");
-    DLQ_CUDA(ctx, cudaMemcpyAsync(m->d_xu8 + n0 * img, x_hwc_host + n0 * img, n * img, cudaMemcpyHostToDevice, m->copy_stream));
-    DLQ_CUDA(ctx, cudaEventRecord(m->copy_done[k], m->copy_stream));
-  }
-  k = 0;
-  for (int n0 = 0; n0 < N; n0 += chunk, ++k) {
-    const int n = std::min(chunk, N - n0);
-    DLQ_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, m->copy_done[k], 0));
-    const int rc = forward_impl(m, nullptr, n, m->d_logits + static_cast<size_t>(n0) * 1000, nullptr, m->d_xu8 + n0 * img);
-    if (rc != DLQ_OK) return rc;
-  }
-  DLQ_CUDA(ctx, cudaMemcpyAsync(logits_host, m->d_logits, static_cast<size_t>(N) * 1000 * sizeof(float),
-                                cudaMemcpyDeviceToHost, ctx->stream));
-  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  m->last_N = std::min(chunk, N - (k - 1) * chunk);
-  return DLQ_OK;
+  return forward_host_sync(m, x_hwc_host, N, logits_host, true);
 }
 
 int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out) {
@@ -930,22 +1155,122 @@ int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out) {
 }  // extern "C"
 
 // ================================================================================================
-// batch-sharded multi-GPU driver: one context + replica per device, one host thread per device per
-// call, contiguous split, logits gathered straight into the caller's host array (no collective).
+// batch-sharded multi-GPU driver: one context + model replica + PERSISTENT host worker thread per device.  Images are
+// split contiguously; every worker drives its device through the pipelined host entry points and writes its logits
+// straight into the caller's host array - no collective.  The same device may be listed more than once
+// (independent replicas on separate streams).
 // ================================================================================================
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
+
 struct dlq_multi {
-  std::vector<dlq_ctx*> ctx;
-  std::vector<dlq_resnet18*> model;
+  struct Worker {
+    dlq_ctx* ctx = nullptr;
+    dlq_resnet18* model = nullptr;
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_done;
+    std::deque<std::function<int()>> jobs;
+    int pending = 0;        // queued + running jobs
+    int rc = DLQ_OK;        // first failure since the last wait
+    bool stop = false;
+  };
+  std::vector<std::unique_ptr<Worker>> w;
   int max_per_dev = 0;
   std::string err;
 };
+
+namespace {
+void worker_loop(dlq_multi::Worker* w) {
+  cudaSetDevice(w->ctx->device);
+  for (;;) {
+    std::function<int()> job;
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      w->cv_job.wait(lk, [&] { return w->stop || !w->jobs.empty(); });
+      if (w->jobs.empty()) return;      // stop requested and nothing left to run
+      job = std::move(w->jobs.front());
+      w->jobs.pop_front();
+    }
+    const int rc = job();
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      if (rc != DLQ_OK && w->rc == DLQ_OK) w->rc = rc;
+      --w->pending;
+    }
+    w->cv_done.notify_all();
+  }
+}
+void post(dlq_multi::Worker* w, std::function<int()> job) {
+  {
+    std::lock_guard<std::mutex> lk(w->mu);
+    w->jobs.push_back(std::move(job));
+    ++w->pending;
+  }
+  w->cv_job.notify_one();
+}
+// wait until every worker is idle; returns the first failure (and clears it)
+int drain(dlq_multi* m) {
+  int first = DLQ_OK;
+  for (size_t g = 0; g < m->w.size(); ++g) {
+    dlq_multi::Worker* w = m->w[g].get();
+    std::unique_lock<std::mutex> lk(w->mu);
+    w->cv_done.wait(lk, [&] { return w->pending == 0; });
+    if (w->rc != DLQ_OK && first == DLQ_OK) {
+      first = w->rc;
+      m->err = std::string("device slot ") + std::to_string(g) + ": " + dlq_last_error_string(w->ctx);
+    }
+    w->rc = DLQ_OK;
+  }
+  return first;
+}
+// contiguous split of N images over G workers: worker g takes [g * ceil(N/G), ...)
+inline void shard_range(int N, int G, int g, int* n0, int* n1) {
+  const int per = (N + G - 1) / G;
+  *n0 = std::min(N, g * per);
+  *n1 = std::min(N, (g + 1) * per);
+}
+int multi_submit(dlq_multi* m, const void* x_host, int N, float* logits_host, bool u8) {
+  if (!m || !x_host || !logits_host || N < 0) return DLQ_ERR_ARG;
+  const int G = static_cast<int>(m->w.size());
+  if ((N + G - 1) / G > m->max_per_dev) {
+    m->err = "batch exceeds n_devices * max_batch_per_device";
+    return DLQ_ERR_ARG;
+  }
+  const size_t elem = u8 ? 1 : sizeof(float);
+  for (int g = 0; g < G; ++g) {
+    int n0, n1;
+    shard_range(N, G, g, &n0, &n1);
+    if (n1 <= n0) continue;
+    dlq_multi::Worker* w = m->w[g].get();
+    const uint8_t* xs = static_cast<const uint8_t*>(x_host) + static_cast<size_t>(n0) * 3 * 224 * 224 * elem;
+    float* ls = logits_host + static_cast<size_t>(n0) * 1000;
+    const int n = n1 - n0;
+    post(w, [w, xs, ls, n, u8]() {
+      return u8 ? dlq_resnet18_submit_host_u8(w->model, xs, n, ls)
+                : dlq_resnet18_submit_host(w->model, reinterpret_cast<const float*>(xs), n, ls);
+    });
+  }
+  return DLQ_OK;
+}
+}  // namespace
 
 extern "C" {
 
 void dlq_multi_destroy(dlq_multi* m) {
   if (!m) return;
-  for (size_t i = 0; i < m->model.size(); ++i) dlq_resnet18_destroy(m->model[i]);
-  for (size_t i = 0; i < m->ctx.size(); ++i) dlq_destroy(m->ctx[i]);
+  for (auto& up : m->w) {
+    dlq_multi::Worker* w = up.get();
+    if (w->th.joinable()) {
+      { std::lock_guard<std::mutex> lk(w->mu); w->stop = true; }
+      w->cv_job.notify_all();
+      w->th.join();
+    }
+    if (w->model) dlq_resnet18_destroy(w->model);
+    if (w->ctx) dlq_destroy(w->ctx);
+  }
   delete m;
 }
 
@@ -956,53 +1281,84 @@ int dlq_multi_create(const int* devices, int n_devices, const dlq_resnet18_weigh
   dlq_multi* m = new dlq_multi();
   m->max_per_dev = max_batch_per_device;
   for (int i = 0; i < n_devices; ++i) {
-    dlq_ctx* c = nullptr;
-    int rc = dlq_create(devices[i], &c);
+    m->w.emplace_back(new dlq_multi::Worker());
+    dlq_multi::Worker* wk = m->w.back().get();
+    int rc = dlq_create(devices[i], &wk->ctx);
+    if (rc == DLQ_OK) {
+      rc = dlq_resnet18_create(wk->ctx, w, max_batch_per_device, &wk->model);
+      if (rc != DLQ_OK) fprintf(stderr, "dlq_multi_create: device %d: %s\n", devices[i], dlq_last_error_string(wk->ctx));
+    }
     if (rc != DLQ_OK) {
       dlq_multi_destroy(m);
       return rc;
     }
-    m->ctx.push_back(c);
-    dlq_resnet18* r = nullptr;
-    rc = dlq_resnet18_create(c, w, max_batch_per_device, &r);
-    if (rc != DLQ_OK) {
-      fprintf(stderr, "dlq_multi_create: device %d: %s\n", devices[i], dlq_last_error_string(c));
-      dlq_multi_destroy(m);
-      return rc;
-    }
-    m->model.push_back(r);
+    wk->th = std::thread(worker_loop, wk);
   }
   *out = m;
   return DLQ_OK;
 }
 
 const char* dlq_multi_last_error_string(const dlq_multi* m) { return m ? m->err.c_str() : "null"; }
+int dlq_multi_n_devices(const dlq_multi* m) { return m ? static_cast<int>(m->w.size()) : 0; }
 
-int dlq_multi_forward_host(dlq_multi* m, const float* x_host, int N, float* logits_host) {
-  if (!m || !x_host || !logits_host || N < 0) return DLQ_ERR_ARG;
-  const int G = static_cast<int>(m->ctx.size());
-  const int per = (N + G - 1) / G;
-  if (per > m->max_per_dev) {
-    m->err = "batch exceeds n_devices * max_batch_per_device";
-    return DLQ_ERR_ARG;
+/* uint8 preprocessing table on every replica (dlq_resnet18_set_preprocess) */
+int dlq_multi_set_preprocess(dlq_multi* m, const float* mean3, const float* std3) {
+  if (!m || !mean3 || !std3) return DLQ_ERR_ARG;
+  for (auto& up : m->w) {
+    dlq_multi::Worker* w = up.get();
+    const float mean[3] = {mean3[0], mean3[1], mean3[2]}, sd[3] = {std3[0], std3[1], std3[2]};
+    post(w, [w, mean, sd]() { return dlq_resnet18_set_preprocess(w->model, mean, sd); });
   }
-  std::vector<int> rc(G, DLQ_OK);
-  std::vector<std::thread> th;
-  for (int g = 0; g < G; ++g) {
-    const int n0 = std::min(N, g * per), n1 = std::min(N, (g + 1) * per);
-    if (n1 <= n0) continue;
-    th.emplace_back([=, &rc]() {
-      rc[g] = dlq_resnet18_forward_host(m->model[g], x_host + static_cast<size_t>(n0) * 3 * 224 * 224, n1 - n0,
-                                        logits_host + static_cast<size_t>(n0) * 1000);
+  return drain(m);
+}
+
+/* asynchronous: the batch is split, every worker enqueues H2D -> forward -> D2H for its share and returns to its queue;
+ * up to two batches per device are in flight (dlq_resnet18_submit_host).  dlq_multi_wait blocks until everything
+ * submitted so far has its logits in host memory. */
+int dlq_multi_submit_host(dlq_multi* m, const float* x_host, int N, float* logits_host) {
+  return multi_submit(m, x_host, N, logits_host, false);
+}
+int dlq_multi_submit_host_u8(dlq_multi* m, const uint8_t* x_hwc_host, int N, float* logits_host) {
+  return multi_submit(m, x_hwc_host, N, logits_host, true);
+}
+int dlq_multi_wait(dlq_multi* m) {
+  if (!m) return DLQ_ERR_ARG;
+  for (auto& up : m->w) {
+    dlq_multi::Worker* w = up.get();
+    post(w, [w]() {
+      int rc = DLQ_OK;
+      while (rc == DLQ_OK && w->model->n_outstanding) rc = dlq_resnet18_wait(w->model);
+      return rc;
     });
   }
-  for (auto& t : th) t.join();
-  for (int g = 0; g < G; ++g)
-    if (rc[g] != DLQ_OK) {
-      m->err = std::string("device ") + std::to_string(g) + ": " + dlq_last_error_string(m->ctx[g]);
-      return rc[g];
-    }
-  return DLQ_OK;
+  return drain(m);
+}
+int dlq_multi_forward_host(dlq_multi* m, const float* x_host, int N, float* logits_host) {
+  const int rc = multi_submit(m, x_host, N, logits_host, false);
+  return rc != DLQ_OK ? rc : dlq_multi_wait(m);
+}
+int dlq_multi_forward_host_u8(dlq_multi* m, const uint8_t* x_hwc_host, int N, float* logits_host) {
+  const int rc = multi_submit(m, x_hwc_host, N, logits_host, true);
+  return rc != DLQ_OK ? rc : dlq_multi_wait(m);
+}
+
+/* device-resident form: x_dev[g] / logits_dev[g] are DEVICE pointers on the g-th listed device holding n_per_dev[g] images
+ * (fp32 NCHW) and room for n_per_dev[g] x 1000 logits; every replica runs its forward and is synchronised.  This is the
+ * driver's compute-only number (no host link in the way). */
+int dlq_multi_forward_device(dlq_multi* m, const float* const* x_dev, const int* n_per_dev, float* const* logits_dev) {
+  if (!m || !x_dev || !n_per_dev || !logits_dev) return DLQ_ERR_ARG;
+  for (size_t g = 0; g < m->w.size(); ++g) {
+    if (n_per_dev[g] <= 0) continue;
+    dlq_multi::Worker* w = m->w[g].get();
+    const float* x = x_dev[g];
+    float* l = logits_dev[g];
+    const int n = n_per_dev[g];
+    post(w, [w, x, l, n]() {
+      const int rc = dlq_resnet18_forward(w->model, x, n, l);
+      return rc != DLQ_OK ? rc : dlq_sync(w->ctx);
+    });
+  }
+  return drain(m);
 }
 
 }  // extern "C"

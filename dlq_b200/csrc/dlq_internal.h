@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,10 +18,26 @@ struct dlq_ctx {
   int num_sms = 148;
   size_t smem_optin = 0;
   std::string err;
-  // grow-only scratch for the per-layer NCHW entry points (never used by the fused network path)
-  void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t scratch_bytes[4] = {0, 0, 0, 0};
+  // workspace of the per-layer NCHW entry points (never used by the fused network path): ONE allocation, sized by
+  // dlq_workspace_reserve() - after which those entry points never allocate - or grown on demand when the caller
+  // never reserved (SURVEY 8b "Ownership"; the reference instead allocates per call, R/infer_e2e.cu:128-130)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  bool ws_reserved = false;
+  void* small = nullptr;    // 256 B of device scratch for reductions (dlq_compare_f32), allocated at dlq_create
+  bool no_pdl = false;      // (TIMING builds only: DLQ_DBG_NO_PDL, read once at dlq_create)
 };
+
+// Tuning / debug switches are honoured only by a library built with `make TIMING=1`; in the product build every
+// lookup is a compile-time nullptr, so no environment variable can change what the library computes or stores.
+static inline const char* dlq_dbg_env(const char* name) {
+#ifdef DLQ_TIMING
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 #define DLQ_CUDA(ctx, call)                                                                  \
   do {                                                                                       \
@@ -79,6 +96,7 @@ struct dlq_conv_weights {
   std::vector<int8_t> q_oihw; // host copy of the quantised weights (tests / checkpoints)
   std::vector<float> scale;   // per-output-channel scale
   int device = 0;
+  int fc_O = 0, fc_I = 0;     // packed by dlq_fc_weights_pack*: the logical [O, I] of the matrix (OC / IC are its padded sizes)
 };
 
 namespace dlq {
@@ -116,16 +134,28 @@ int nchw_to_act_i8(dlq_ctx* ctx, const int8_t* x, const Act& a);          // den
 int act_to_nchw_i8(dlq_ctx* ctx, const Act& a, int8_t* y);                // row-padded NHWC -> dense NCHW
 int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32_t* y);
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a);   // C=3 int8 NCHW -> s2d
-int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a, int fp8 = 0);
-int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a);
-int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out);
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_scale, const Act& a, int fp8 = 0,
+                       unsigned long long* stamp = nullptr);
+int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a,
+                      unsigned long long* stamp = nullptr);
+int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out, unsigned long long* stamp = nullptr);
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
+               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits,
+               unsigned long long* stamp = nullptr);
 
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
                     const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
 
-void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes);
+// dlq_api.cu: per-row symmetric quantisation of a [rows, K] fp32 matrix (QUANT_SPEC 1 / 6), host
+void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s);
+void quantize_rows_e4m3(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s);
+
+// workspace: make sure ctx->ws holds `bytes`; DLQ_OK, DLQ_ERR_ARG (reserved workspace too small) or DLQ_ERR_CUDA (OOM)
+int ctx_workspace(dlq_ctx* ctx, size_t bytes);
 float inv_scale(float s);
+// per-device kernel attributes (max dynamic shared memory), set once per context in dlq_create; also proves that the
+// sm_100a images load on this device
+int configure_conv_kernels(dlq_ctx* ctx);
+int configure_elementwise_kernels(dlq_ctx* ctx);
 
 }  // namespace dlq

@@ -11,34 +11,35 @@ namespace dlq {
 
 float inv_scale(float s) { return static_cast<float>(1.0 / static_cast<double>(s)); }
 
-void* ctx_scratch(dlq_ctx* ctx, int slot, size_t bytes) {
-  if (ctx->scratch_bytes[slot] < bytes) {
-    if (ctx->scratch[slot]) {
-      cudaStreamSynchronize(ctx->stream);
-      cudaFree(ctx->scratch[slot]);
-    }
-    ctx->scratch[slot] = nullptr;
-    ctx->scratch_bytes[slot] = 0;
-    if (cudaMalloc(&ctx->scratch[slot], bytes) != cudaSuccess) return nullptr;
-    ctx->scratch_bytes[slot] = bytes;
+int ctx_workspace(dlq_ctx* ctx, size_t bytes) {
+  if (ctx->ws_bytes >= bytes) return DLQ_OK;
+  DLQ_ARG(ctx, !ctx->ws_reserved, "workspace too small for this call: reserve dlq_conv2d_workspace_bytes() with dlq_workspace_reserve()");
+  // not reserved by the caller: grow (synchronises; callers that must not allocate on the hot path reserve first)
+  if (ctx->ws) {
+    DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
   }
-  return ctx->scratch[slot];
+  DLQ_CUDA(ctx, cudaMalloc(&ctx->ws, bytes));
+  ctx->ws_bytes = bytes;
+  return DLQ_OK;
 }
 
 // launch with cudaLaunchAttributeProgrammaticStreamSerialization (the kernel must call pdl_wait() before it reads
 // anything a previous kernel wrote)
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+static cudaError_t launch_pdl(dlq_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
+  cfg.stream = ctx->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = getenv("DLQ_DBG_NO_PDL") ? 0 : 1;
+  cfg.numAttrs = ctx->no_pdl ? 0 : 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -46,6 +47,26 @@ static inline int grid_for(dlq_ctx* ctx, size_t work_items, int threads, int max
   const size_t blocks = (work_items + threads - 1) / threads;
   const size_t cap = static_cast<size_t>(ctx->num_sms) * max_waves;
   return static_cast<int>(std::max<size_t>(1, std::min(blocks, cap)));
+}
+
+
+// span stamps (bench.py roofline): min globaltimer at block entry, max at block exit, one atomic per block at each end
+__device__ __forceinline__ void stamp_entry(unsigned long long* stamp) {
+  if (stamp && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    atomicMin(stamp, gt);
+  }
+}
+__device__ __forceinline__ void stamp_exit(unsigned long long* stamp) {
+  if (stamp) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+      atomicMax(stamp + 1, gt);
+    }
+  }
 }
 
 __device__ __forceinline__ int quant_rn(float t, int lo, int hi) {
@@ -206,8 +227,9 @@ __global__ void nhwc_to_nchw_i32_kernel(const int32_t* __restrict__ x, int32_t* 
 // QMODE: 0 = copy int8 bytes, 1 = quantise fp32 -> int8 (QUANT_SPEC 2), 2 = quantise fp32 -> E4M3 (QUANT_SPEC 6)
 template <typename T, int QMODE>
 __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
-                                float inv_s) {
+                                float inv_s, unsigned long long* stamp) {
   const int H2 = H / 2, W2 = W / 2, WP = W2 + 3;
+  stamp_entry(stamp);
   pdl_launch_dependents();
   pdl_wait();          // (programmatic dependent launch: the previous kernel on the stream may still be draining)
   const size_t total = static_cast<size_t>(N) * H2 * W2;
@@ -248,6 +270,7 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
     prow[(w2 + 2) * 2 + 0] = o;
     prow[(w2 + 1) * 2 + 1] = o;
   }
+  stamp_exit(stamp);
 }
 
 
@@ -257,8 +280,9 @@ __global__ void stem_s2d_kernel(const T* __restrict__ x, int8_t* __restrict__ a,
 // ((u / 255 - mean) / std, then QUANT_SPEC 2 or 6), so the kernel is a byte gather: 150 KB read per image
 // instead of 602 KB of fp32.
 __global__ void stem_s2d_u8_kernel(const uint8_t* __restrict__ x, int8_t* __restrict__ a, int N, int H, int W, int PR,
-                                   const uint8_t* __restrict__ lut_g) {
+                                   const uint8_t* __restrict__ lut_g, unsigned long long* stamp) {
   __shared__ uint8_t lut[3 * 256];
+  stamp_entry(stamp);
   for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut_g[i];
   pdl_launch_dependents();
   pdl_wait();
@@ -286,6 +310,7 @@ __global__ void stem_s2d_u8_kernel(const uint8_t* __restrict__ x, int8_t* __rest
     prow[(w2 + 2) * 2 + 0] = v;
     prow[(w2 + 1) * 2 + 1] = v;
   }
+  stamp_exit(stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -450,8 +475,9 @@ __global__ void maxpool_act_kernel(const int8_t* __restrict__ in, int8_t* __rest
 template <int TR>
 __global__ void __launch_bounds__(256, 1)
 maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int N, int H, int W, int C, int PRi, int OH,
-                    int OW, int PRo) {
+                    int OW, int PRo, unsigned long long* stamp) {
   extern __shared__ __align__(128) uint8_t pool_smem[];
+  stamp_entry(stamp);
   __shared__ __align__(8) uint64_t full[2];
   constexpr int kSlabRows = 2 * TR + 1;
   const size_t row_bytes = static_cast<size_t>(W) * C;
@@ -533,6 +559,7 @@ maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int
     }
     __syncthreads();      // everyone is done reading this buffer before it is refilled (two iterations ahead)
   }
+  stamp_exit(stamp);
 }
 
 // max-pool on dense NCHW int8 (per-layer ABI entry)
@@ -574,8 +601,10 @@ constexpr int kGapOSplit = 2;
 __global__ void __launch_bounds__(512)
 gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
               float inv_gap_scale, const int8_t* __restrict__ fc_w, const float* __restrict__ fc_scale,
-              const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits) {
+              const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits,
+              unsigned long long* stamp) {
   extern __shared__ int4 smem_gap[];
+  stamp_entry(stamp);
   int32_t* part_sum = reinterpret_cast<int32_t*>(smem_gap);                                 // [imgs][parts][C]
   int8_t* sg = reinterpret_cast<int8_t*>(part_sum + kGapImgs * kGapParts * C);              // [imgs][C]
   const int n0 = blockIdx.x * kGapImgs;
@@ -617,7 +646,7 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
     if (gap_q && blockIdx.y == 0) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
   }
   __syncthreads();
-  if (!logits) return;
+  if (!logits) { stamp_exit(stamp); return; }
   // phase 2: FC.  fc_wT is the weight matrix pre-transposed on the host to [C/16][Opad][16 B] so that
   // consecutive threads (= consecutive outputs) read consecutive 16-byte chunks; the pooled activations are
   // broadcast from shared memory.  One thread = one output row for all images of the CTA, no shuffles.
@@ -645,6 +674,7 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
     for (int im = 0; im < kGapImgs; ++im)
       if (im < nimg) logits[static_cast<size_t>(n0 + im) * O + o] = __fmaf_rn((float)acc[im], sc, bi);
   }
+  stamp_exit(stamp);
 }
 
 // standalone GAP on dense NCHW int8: one warp per (n,c)
@@ -810,43 +840,39 @@ int nhwc_to_nchw_i32(dlq_ctx* ctx, const int32_t* x, int N, int C, int HW, int32
 int nchw_i8_to_stem_s2d(dlq_ctx* ctx, const int8_t* x, int N, int H, int W, const Act& a) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
-  stem_s2d_kernel<int8_t, 0><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f);
+  stem_s2d_kernel<int8_t, 0><<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(x, a.ptr, N, H, W, a.PR, 1.f, nullptr);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
-int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a, int fp8) {
+int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float inv_s, const Act& a, int fp8,
+                       unsigned long long* stamp) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
   const int grid = grid_for(ctx, total, 256);
-  if (fp8) DLQ_CUDA(ctx, launch_pdl(stem_s2d_kernel<float, 2>, dim3(grid), dim3(256), 0, ctx->stream, x, a.ptr, N, H, W, a.PR, inv_s));
-  else DLQ_CUDA(ctx, launch_pdl(stem_s2d_kernel<float, 1>, dim3(grid), dim3(256), 0, ctx->stream, x, a.ptr, N, H, W, a.PR, inv_s));
+  if (fp8) DLQ_CUDA(ctx, launch_pdl(ctx, stem_s2d_kernel<float, 2>, dim3(grid), dim3(256), 0, x, a.ptr, N, H, W, a.PR, inv_s, stamp));
+  else DLQ_CUDA(ctx, launch_pdl(ctx, stem_s2d_kernel<float, 1>, dim3(grid), dim3(256), 0, x, a.ptr, N, H, W, a.PR, inv_s, stamp));
   return DLQ_OK;
 }
-int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a) {
+int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a,
+                      unsigned long long* stamp) {
   DLQ_ARG(ctx, H % 2 == 0 && W % 2 == 0 && a.H == H / 2 && a.W == W / 2 + 3 && a.C == 32, "stem s2d geometry");
   const size_t total = static_cast<size_t>(N) * a.H * (W / 2);
-  DLQ_CUDA(ctx, launch_pdl(stem_s2d_u8_kernel, dim3(grid_for(ctx, total, 256)), dim3(256), 0, ctx->stream, x_hwc, a.ptr, N, H, W,
-                           a.PR, lut_dev));
+  DLQ_CUDA(ctx, launch_pdl(ctx, stem_s2d_u8_kernel, dim3(grid_for(ctx, total, 256)), dim3(256), 0, x_hwc, a.ptr, N, H, W,
+                           a.PR, lut_dev, stamp));
   return DLQ_OK;
 }
-int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
+int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out, unsigned long long* stamp) {
   DLQ_ARG(ctx, in.C % 16 == 0 && out.C == in.C && out.N == in.N, "maxpool geometry");
   // staged path: 4 output rows per tile, two slabs of 9 input rows in shared memory
   {
     constexpr int TR = 4;
     const size_t row_bytes = static_cast<size_t>(in.W) * in.C;
     const size_t smem = 2 * (2 * TR + 1) * row_bytes;
-    if (smem <= ctx->smem_optin - 4096 && row_bytes % 16 == 0 && in.H >= 2 && !getenv("DLQ_DBG_POOL_DIRECT")) {
-      static bool configured[16] = {false};
-      if (!configured[ctx->device & 15]) {
-        DLQ_CUDA(ctx, cudaFuncSetAttribute(maxpool_rows_kernel<TR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(ctx->smem_optin - 4096)));
-        configured[ctx->device & 15] = true;
-      }
+    if (smem <= ctx->smem_optin - 4096 && row_bytes % 16 == 0 && in.H >= 2 && !dlq_dbg_env("DLQ_DBG_POOL_DIRECT")) {
       const int n_tiles = in.N * ((out.H + TR - 1) / TR);
       const int grid = std::max(1, std::min(n_tiles, ctx->num_sms));
-      DLQ_CUDA(ctx, launch_pdl(maxpool_rows_kernel<TR>, dim3(grid), dim3(256), smem, ctx->stream,
-                               static_cast<const int8_t*>(in.ptr), out.ptr, in.N, in.H, in.W, in.C, in.PR, out.H, out.W, out.PR));
+      DLQ_CUDA(ctx, launch_pdl(ctx, maxpool_rows_kernel<TR>, dim3(grid), dim3(256), smem,
+                               static_cast<const int8_t*>(in.ptr), out.ptr, in.N, in.H, in.W, in.C, in.PR, out.H, out.W, out.PR, stamp));
       return DLQ_OK;
     }
   }
@@ -854,6 +880,11 @@ int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out) {
   maxpool_act_kernel<<<grid_for(ctx, total, 256), 256, 0, ctx->stream>>>(in.ptr, out.ptr, in.N, in.H, in.W, in.C, in.PR,
                                                                          out.H, out.W, out.PR);
   DLQ_CUDA(ctx, cudaGetLastError());
+  return DLQ_OK;
+}
+int configure_elementwise_kernels(dlq_ctx* ctx) {
+  DLQ_CUDA(ctx, cudaFuncSetAttribute(maxpool_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(ctx->smem_optin - 4096)));
   return DLQ_OK;
 }
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
@@ -865,13 +896,13 @@ int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_
   return DLQ_OK;
 }
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits) {
+               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned long long* stamp) {
   DLQ_ARG(ctx, in.C % 512 == 0 || in.C % 16 == 0, "gap channels");
   DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
   const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
   const size_t gap_smem = static_cast<size_t>(kGapImgs) * kGapParts * in.C * 4 + static_cast<size_t>(kGapImgs) * in.C;
-  DLQ_CUDA(ctx, launch_pdl(gap_fc_kernel, dim3(blocks, logits ? kGapOSplit : 1), dim3(512), gap_smem, ctx->stream, static_cast<const int8_t*>(in.ptr),
-                           in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits));
+  DLQ_CUDA(ctx, launch_pdl(ctx, gap_fc_kernel, dim3(blocks, logits ? kGapOSplit : 1), dim3(512), gap_smem, static_cast<const int8_t*>(in.ptr),
+                           in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits, stamp));
   return DLQ_OK;
 }
 

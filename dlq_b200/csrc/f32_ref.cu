@@ -408,8 +408,7 @@ int dlq_topk_f32(dlq_ctx* ctx, const float* x, int N, int K, int k, int* idx, fl
 int dlq_compare_f32(dlq_ctx* ctx, const float* a, const float* b, size_t n, double* out3) {
   if (!ctx) return DLQ_ERR_ARG;
   DLQ_ARG(ctx, a && b && out3 && n > 0, "null pointer or empty tensor");
-  double* d = static_cast<double*>(ctx_scratch(ctx, 3, 5 * sizeof(double)));
-  DLQ_ARG(ctx, d, "out of device memory");
+  double* d = static_cast<double*>(ctx->small);
   DLQ_CUDA(ctx, cudaMemsetAsync(d, 0, 5 * sizeof(double), ctx->stream));
   compare_f32_kernel<<<296, 256, 0, ctx->stream>>>(a, b, n, d);
   double h[5];

@@ -1,7 +1,7 @@
 // dlq_bench — throughput / latency of the INT8 (or FP8) ResNet-18 path measured from C++ through the C ABI only
 // (no Python, no torch): the host-language counterpart of bench.py for the reference's C++ users.
 //
-//   dlq_bench [--weights DIR] [--batch 256] [--iters 50] [--warmup 10] [--fp8] [--gpus G]
+//   dlq_bench [--weights DIR] [--batch 256] [--iters 50] [--warmup 10] [--fp8] [--gpus G | --devices 0,1,..]
 //
 // --weights DIR : weight directory in the reference's export format (tools/export_resnet18.py:85-92), with or without
 //                 the quant block; without it (and without --weights at all: synthetic weights, the recipe of
@@ -9,8 +9,9 @@
 //                 reference's FP32 arithmetic on the GPU.
 // one GPU  : device-resident images/s (cudaEvents on the library's stream), host-buffer images/s
 //            (dlq_resnet18_forward_host from pinned memory, H2D + D2H inside the timed region), batch-1 CUDA-graph latency.
-// --gpus G : BASELINE config 4 - `batch` images split over G devices by the batch-sharded driver (dlq_multi_*), host
-//            buffers in, logits gathered on the host, wall-clock.
+// --gpus G : BASELINE config 4 - `batch` images split over G devices by the batch-sharded driver (dlq_multi_*): host
+//            buffers in, logits gathered on the host, wall-clock (synchronous, pipelined fp32, pipelined uint8) and the
+//            device-resident number.  --devices lists them explicitly (a device may repeat).
 // Prints one JSON line.  Exit codes: 1 usage / IO, 3 CUDA or library error.
 #include <cuda_runtime.h>
 
@@ -100,6 +101,7 @@ int main(int argc, char** argv) {
   std::string wdir;
   int batch = 256, iters = 50, warmup = 10, gpus = 1;
   bool fp8 = false;
+  std::vector<int> devlist;      // --devices 0,0 : explicit device list (a device may repeat: independent replicas)
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--weights" && i + 1 < argc) wdir = argv[++i];
@@ -107,8 +109,12 @@ int main(int argc, char** argv) {
     else if (a == "--iters" && i + 1 < argc) iters = atoi(argv[++i]);
     else if (a == "--warmup" && i + 1 < argc) warmup = atoi(argv[++i]);
     else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
+    else if (a == "--devices" && i + 1 < argc) {
+      for (const char* p = argv[++i]; *p;) { devlist.push_back(atoi(p)); while (*p && *p != ',') ++p; if (*p) ++p; }
+      gpus = static_cast<int>(devlist.size());
+    }
     else if (a == "--fp8") fp8 = true;
-    else { fprintf(stderr, "usage: dlq_bench [--weights DIR] [--batch B] [--iters K] [--warmup W] [--fp8] [--gpus G]\n"); return 1; }
+    else { fprintf(stderr, "usage: dlq_bench [--weights DIR] [--batch B] [--iters K] [--warmup W] [--fp8] [--gpus G | --devices a,b,..]\n"); return 1; }
   }
   if (batch < 1 || iters < 1 || warmup < 0 || gpus < 1 || batch % gpus) { fprintf(stderr, "bad batch / iters / gpus\n"); return 1; }
 
@@ -156,23 +162,69 @@ int main(int argc, char** argv) {
   CK_CUDA(cudaMallocHost(&hl, static_cast<size_t>(batch) * 1000 * 4));
   for (int n = 0; n < batch; ++n) memcpy(hx + static_cast<size_t>(n) * kImg, img8.data() + static_cast<size_t>(n % 8) * kImg, kImg * 4);
 
-  if (gpus > 1) {
-    // ---- batch-sharded over G devices (host in, host out, wall-clock)
+  if (gpus > 1 || !devlist.empty()) {
+    // ---- BASELINE config 4: `batch` images split over G devices by the batch-sharded driver.  Four numbers: host fp32
+    // (synchronous call per batch), host fp32 / uint8 pipelined (submit k+1 while k runs; "all devices start -> logits
+    // gathered on host", wall clock), and device-resident (compute only).
     std::vector<int> dev(gpus);
-    for (int g = 0; g < gpus; ++g) dev[g] = g;
+    for (int g = 0; g < gpus; ++g) dev[g] = devlist.empty() ? g : devlist[g];
     dlq_multi* mm = nullptr;
     if (dlq_multi_create(dev.data(), gpus, &W, batch / gpus, &mm) != DLQ_OK) { fprintf(stderr, "dlq_multi_create failed\n"); return 3; }
-    for (int i = 0; i < std::max(1, warmup); ++i)
-      if (dlq_multi_forward_host(mm, hx, batch, hl) != DLQ_OK) { fprintf(stderr, "%s\n", dlq_multi_last_error_string(mm)); return 3; }
-    const auto t0 = std::chrono::steady_clock::now();
-    for (int i = 0; i < iters; ++i)
-      if (dlq_multi_forward_host(mm, hx, batch, hl) != DLQ_OK) { fprintf(stderr, "%s\n", dlq_multi_last_error_string(mm)); return 3; }
-    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    int top0 = static_cast<int>(std::max_element(hl, hl + 1000) - hl);
-    printf("{\"driver\": \"dlq_bench (C++)\", \"dtype\": \"%s\", \"n_gpus\": %d, \"global_batch\": %d, \"batch_per_gpu\": %d, "
-           "\"iters\": %d, \"host_images_per_s\": %.1f, \"ms_per_batch\": %.4f, \"top1_image0\": %d, "
-           "\"how\": \"dlq_multi_forward_host: pinned fp32 host batch split over the devices, logits gathered on the host, wall clock\"}\n",
-           fp8 ? "e4m3" : "s8", gpus, batch, batch / gpus, iters, batch * static_cast<double>(iters) / sec, 1e3 * sec / iters, top0);
+#define CK_MULTI(call) do { if ((call) != DLQ_OK) { fprintf(stderr, "%s\n", dlq_multi_last_error_string(mm)); return 3; } } while (0)
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    // (1) synchronous fp32 host batches
+    for (int i = 0; i < std::max(1, warmup); ++i) CK_MULTI(dlq_multi_forward_host(mm, hx, batch, hl));
+    auto t0 = now();
+    for (int i = 0; i < iters; ++i) CK_MULTI(dlq_multi_forward_host(mm, hx, batch, hl));
+    const double sec_sync = secs(t0);
+    const int top0 = static_cast<int>(std::max_element(hl, hl + 1000) - hl);
+    // (2) pipelined fp32 host batches
+    t0 = now();
+    for (int i = 0; i < iters; ++i) CK_MULTI(dlq_multi_submit_host(mm, hx, batch, hl));
+    CK_MULTI(dlq_multi_wait(mm));
+    const double sec_pipe = secs(t0);
+    // (3) pipelined uint8 host batches (ImageNet mean / std table on the device)
+    uint8_t* hu = nullptr;
+    CK_CUDA(cudaMallocHost(&hu, static_cast<size_t>(batch) * kImg));
+    for (size_t i = 0; i < static_cast<size_t>(batch) * kImg; ++i) hu[i] = static_cast<uint8_t>((i * 2654435761u) >> 24);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    CK_MULTI(dlq_multi_set_preprocess(mm, mean, sd));
+    CK_MULTI(dlq_multi_forward_host_u8(mm, hu, batch, hl));
+    t0 = now();
+    for (int i = 0; i < iters; ++i) CK_MULTI(dlq_multi_submit_host_u8(mm, hu, batch, hl));
+    CK_MULTI(dlq_multi_wait(mm));
+    const double sec_u8 = secs(t0);
+    // (4) device-resident shards
+    std::vector<const float*> dxs(gpus);
+    std::vector<float*> dls(gpus);
+    std::vector<int> per(gpus, batch / gpus);
+    for (int g = 0; g < gpus; ++g) {
+      CK_CUDA(cudaSetDevice(dev[g]));
+      float* p = nullptr;
+      CK_CUDA(cudaMalloc(&p, static_cast<size_t>(per[g]) * kImg * 4));
+      CK_CUDA(cudaMemcpy(p, hx + static_cast<size_t>(g) * per[g] * kImg, static_cast<size_t>(per[g]) * kImg * 4, cudaMemcpyHostToDevice));
+      dxs[g] = p;
+      CK_CUDA(cudaMalloc(&dls[g], static_cast<size_t>(per[g]) * 1000 * 4));
+    }
+    for (int i = 0; i < 3; ++i) CK_MULTI(dlq_multi_forward_device(mm, dxs.data(), per.data(), dls.data()));
+    t0 = now();
+    for (int i = 0; i < iters; ++i) CK_MULTI(dlq_multi_forward_device(mm, dxs.data(), per.data(), dls.data()));
+    const double sec_dev = secs(t0);
+    for (int g = 0; g < gpus; ++g) { cudaSetDevice(dev[g]); cudaFree(const_cast<float*>(dxs[g])); cudaFree(dls[g]); }
+    std::string devs;
+    for (int g = 0; g < gpus; ++g) devs += (g ? "," : "") + std::to_string(dev[g]);
+    const double B = static_cast<double>(batch) * iters;
+    printf("{\"driver\": \"dlq_bench (C++)\", \"dtype\": \"%s\", \"n_gpus\": %d, \"devices\": [%s], \"global_batch\": %d, "
+           "\"batch_per_gpu\": %d, \"iters\": %d, \"host_images_per_s\": %.1f, \"host_pipelined_images_per_s\": %.1f, "
+           "\"host_u8_pipelined_images_per_s\": %.1f, \"device_resident_images_per_s\": %.1f, \"ms_per_batch\": %.4f, "
+           "\"top1_image0\": %d, "
+           "\"how\": \"dlq_multi_*: persistent worker thread per device, pinned host batch split contiguously, logits written "
+           "straight into one host array, wall clock; pipelined = submit k+1 while k runs; device-resident = one synchronised "
+           "forward per replica and iteration\"}\n",
+           fp8 ? "e4m3" : "s8", gpus, devs.c_str(), batch, batch / gpus, iters, B / sec_sync, B / sec_pipe, B / sec_u8, B / sec_dev,
+           1e3 * sec_sync / iters, top0);
+    cudaFreeHost(hu);
     dlq_multi_destroy(mm);
   } else {
     dlq_resnet18* net = nullptr;
@@ -200,6 +252,21 @@ int main(int argc, char** argv) {
     for (int i = 0; i < hiters; ++i) CK_DLQ(ctx, dlq_resnet18_forward_host(net, hx, batch, hl));
     const double hsec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     const int top0 = static_cast<int>(std::max_element(hl, hl + 1000) - hl);
+    // host buffers, pipelined uint8 images: submit k+1 while k runs
+    uint8_t* hu = nullptr;
+    CK_CUDA(cudaMallocHost(&hu, static_cast<size_t>(batch) * kImg));
+    for (size_t i = 0; i < static_cast<size_t>(batch) * kImg; ++i) hu[i] = static_cast<uint8_t>((i * 2654435761u) >> 24);
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, sd[3] = {0.229f, 0.224f, 0.225f};
+    CK_DLQ(ctx, dlq_resnet18_set_preprocess(net, mean, sd));
+    CK_DLQ(ctx, dlq_resnet18_forward_host_u8(net, hu, batch, hl));
+    const auto t1 = std::chrono::steady_clock::now();
+    for (int i = 0; i < hiters; ++i) {
+      CK_DLQ(ctx, dlq_resnet18_submit_host_u8(net, hu, batch, hl));
+      if (i > 0) CK_DLQ(ctx, dlq_resnet18_wait(net));
+    }
+    CK_DLQ(ctx, dlq_resnet18_wait(net));
+    const double usec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    cudaFreeHost(hu);
     // batch-1 latency, CUDA graph
     dlq_resnet18* net1 = nullptr;
     CK_DLQ(ctx, dlq_resnet18_create(ctx, &W, 1, &net1));
@@ -213,12 +280,14 @@ int main(int argc, char** argv) {
     float lat_ms = 0.f;
     CK_CUDA(cudaEventElapsedTime(&lat_ms, e0, e1));
     printf("{\"driver\": \"dlq_bench (C++)\", \"dtype\": \"%s\", \"n_gpus\": 1, \"batch\": %d, \"iters\": %d, "
-           "\"images_per_s\": %.1f, \"ms_per_step\": %.4f, \"host_images_per_s\": %.1f, \"latency_b1_us\": %.1f, "
+           "\"images_per_s\": %.1f, \"ms_per_step\": %.4f, \"host_images_per_s\": %.1f, \"host_u8_pipelined_images_per_s\": %.1f, "
+           "\"latency_b1_us\": %.1f, "
            "\"launches_per_forward\": %d, \"top1_image0\": %d, "
            "\"how\": \"device-resident: cudaEvents on the library stream; host: dlq_resnet18_forward_host from pinned memory, "
            "wall clock; latency: 200 back-to-back CUDA-graph replays at batch 1\"}\n",
            fp8 ? "e4m3" : "s8", batch, iters, batch * static_cast<double>(iters) / (ms * 1e-3), ms / iters,
-           batch * static_cast<double>(hiters) / hsec, 1e3 * lat_ms / 200, dlq_resnet18_launches(net), top0);
+           batch * static_cast<double>(hiters) / hsec, batch * static_cast<double>(hiters) / usec, 1e3 * lat_ms / 200,
+           dlq_resnet18_launches_for_batch(net, batch), top0);
     dlq_resnet18_destroy(net1);
     dlq_resnet18_destroy(net);
     cudaFree(dx); cudaFree(dl);

@@ -12,8 +12,15 @@
  *     (the reference's exit codes, R/utils.hpp:34-45; 2 stays reserved for parity failures in tests);
  *     dlq_last_error_string() gives the text.  Nothing here ever calls exit().
  *   - all tensor pointers are DEVICE pointers unless the name says host; the caller owns every buffer.
- *   - calls enqueue work on the context's stream and return without synchronising.
- *   - one context per device; a context is not thread-safe, different contexts are independent.
+ *   - calls enqueue work on the context's stream and return without synchronising.  The context's own stream is
+ *     NON-BLOCKING: it has no implicit ordering with the legacy default stream or any other stream.  Buffers the caller
+ *     fills or zeroes on another stream must be complete (event / synchronise) before a call that touches them, or the
+ *     caller adopts its own stream with dlq_set_stream().
+ *   - one context per device; a context is not thread-safe, different contexts are independent (no shared static
+ *     state: kernel attributes are set per context in dlq_create).
+ *   - no entry point allocates device memory after set-up: models allocate at create (host-staging buffers at the first
+ *     host-buffer call), the per-layer NCHW entry points use the context workspace (dlq_workspace_reserve).
+ *   - allocation failures and CUDA runtime errors return 3, argument errors 1.
  *   - quantisation arithmetic is defined by spec/QUANT_SPEC.md (the reference defines none).
  */
 #ifndef DLQ_H
@@ -41,6 +48,13 @@ int dlq_sync(dlq_ctx* ctx);
 void* dlq_stream(dlq_ctx* ctx);                 /* the cudaStream_t work is enqueued on */
 int dlq_set_stream(dlq_ctx* ctx, void* stream); /* adopt a caller-owned cudaStream_t */
 const char* dlq_version(void);
+/* Workspace of the per-layer NCHW entry points (dlq_conv2d_i8 / _fp8, dlq_fc_forward_*_tc): the reference's
+ * conv2d_nchw_im2col_gemm allocates and frees three buffers per call (R/infer_e2e.cu:128-130); here the caller reserves
+ * once - max over its calls of dlq_conv2d_workspace_bytes() / dlq_fc_workspace_bytes() - and those entry points never
+ * allocate (a call that needs more then fails with 1).  Without a reservation the workspace grows on demand
+ * (synchronising), which is convenient for tests, not for a hot path. */
+int dlq_workspace_reserve(dlq_ctx* ctx, size_t bytes);
+size_t dlq_workspace_bytes(const dlq_ctx* ctx); /* current size */
 
 /* ------------------------------------------------------------------ quantise / dequantise helpers
  * (absent from the reference — SURVEY §8 a13; arithmetic per QUANT_SPEC §2) */
@@ -104,6 +118,9 @@ float dlq_res_mul(float s_r, float s_y);
 int dlq_conv2d_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W, const dlq_conv_weights* w,
                   const dlq_epilogue* ep, int8_t* y, int32_t* acc_out, int* OH, int* OW);
 
+/* workspace bytes the call above needs for this shape (see dlq_workspace_reserve) */
+size_t dlq_conv2d_workspace_bytes(const dlq_conv_weights* w, int N, int H, int W, int has_residual, int want_acc);
+
 /* Same operator on E4M3 bytes (weights from dlq_conv_weights_pack_fp8/_e4m3): t = fmaf(acc_f32, alpha, beta) [+ residual],
  * y = e4m3(relu ? max(t, 0) : t); acc_out receives the raw FP32 accumulators.  FP32 accumulation order inside the
  * tensor core is unspecified, so parity with the oracle is by tolerance (QUANT_SPEC 6), not bit-exact. */
@@ -159,6 +176,22 @@ int dlq_gap_global_i8(dlq_ctx* ctx, const int8_t* x, int N, int C, int H, int W,
  * logits = fmaf((float)acc, scale[o], bias[o]) */
 int dlq_fc_forward_i8(dlq_ctx* ctx, const int8_t* g, const int8_t* w, const float* scale, const float* bias, int N,
                       int O, int I, float* logits);
+/* The same FC on the tensor cores (SURVEY 8f-4 "INT8/FP8 FC with the same GEMM core"): the layer is the 1x1
+ * convolution of an [N,1,1,I] tensor, so it runs on the conv kernel (TMA + tcgen05.mma + TMEM) with an fp32 epilogue
+ * logits = fmaf((float)acc, scale[o], bias[o]) - bit-identical to dlq_fc_forward_i8.  Weights are packed once from the
+ * reference's [O, I] row-major layout (HOST pointers); I is padded to 64 / a multiple of 128 and O to a multiple of
+ * 64 internally (max I 2048).  dlq_fc_weights_pack quantises fp32 rows per QUANT_SPEC 1 (fp8 = 0) or 6 (fp8 = 1) and
+ * returns the row scales.  Free with dlq_conv_weights_free. */
+int dlq_fc_weights_pack(dlq_ctx* ctx, const float* w_host, int O, int I, int fp8, float* w_scale_host,
+                        dlq_conv_weights** out);
+int dlq_fc_weights_pack_i8(dlq_ctx* ctx, const int8_t* wq_host, int O, int I, dlq_conv_weights** out);
+int dlq_fc_weights_pack_e4m3(dlq_ctx* ctx, const uint8_t* wq_host, int O, int I, dlq_conv_weights** out);
+size_t dlq_fc_workspace_bytes(const dlq_conv_weights* w, int N);
+int dlq_fc_forward_i8_tc(dlq_ctx* ctx, const int8_t* g, const dlq_conv_weights* w, const float* scale, const float* bias,
+                         int N, float* logits);
+/* E4M3 x E4M3 with FP32 accumulation (kind::f8f6f4); parity by tolerance (QUANT_SPEC 6-7) */
+int dlq_fc_forward_fp8(dlq_ctx* ctx, const uint8_t* g, const dlq_conv_weights* w, const float* scale, const float* bias,
+                       int N, float* logits);
 /* K/softmax.cu:6-47 — row softmax over [N,K] fp32 logits (optional head; uses expf) */
 int dlq_softmax_f32(dlq_ctx* ctx, const float* x, int N, int K, float* y);
 
@@ -202,8 +235,25 @@ int dlq_resnet18_checkpoint(dlq_resnet18* m, const char* name, int8_t* out);
  * context's stream and does not synchronise. */
 int dlq_resnet18_graph_capture(dlq_resnet18* m, const float* x, int N, float* logits);
 int dlq_resnet18_graph_launch(dlq_resnet18* m);
-/* number of kernel launches one forward enqueues (for accounting) */
+/* Pipelined host-buffer form: submit enqueues H2D -> forward of the WHOLE batch -> D2H and returns; up to two submits may
+ * be in flight (double-buffered staging), so the copy of batch k+1 overlaps the forward of batch k and the logits copy of
+ * batch k-1.  dlq_resnet18_wait blocks until the OLDEST outstanding submit's logits are in host memory (no-op when
+ * nothing is outstanding).  x_host / logits_host must stay valid until the matching wait; use pinned memory. */
+int dlq_resnet18_submit_host(dlq_resnet18* m, const float* x_host, int N, float* logits_host);
+int dlq_resnet18_submit_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int N, float* logits_host);
+int dlq_resnet18_wait(dlq_resnet18* m);
+/* profile slots of one forward (dlq_resnet18_profile / _read_stamps): 23 = quantise, 20 convs, max-pool, GAP+FC */
 int dlq_resnet18_launches(const dlq_resnet18* m);
+/* kernels a forward of batch N really launches: 23, or 20 when the three 1x1 shortcut convs ride on conv1's launch
+ * (N <= 16) */
+int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
+/* Span stamps (measurement): with a ring of `ring_forwards` entries, every kernel of a forward records the globaltimer
+ * (ns) of its first block entry and last block exit - its span INSIDE a running sequence of forwards, overlap with its
+ * neighbours included, which an event between launches cannot see.  dlq_resnet18_read_stamps synchronises, copies
+ * [ring][dlq_resnet18_launches()][2] = (entry, exit) to HOST memory (entry == UINT64_MAX: slot not written), reports how
+ * many forwards were recorded and resets the ring.  ring_forwards = 0 switches the stamps off. */
+int dlq_resnet18_enable_stamps(dlq_resnet18* m, int ring_forwards);
+int dlq_resnet18_read_stamps(dlq_resnet18* m, unsigned long long* out_host, int* forwards_recorded);
 /* one forward with a CUDA event between launches; ms[dlq_resnet18_launches()] receives each launch's device
  * time in order: quantise+s2d, stem conv, max-pool, per block conv1,[downsample],conv2, GAP+FC.  Synchronises.
  * (the reference brackets every launch with its cudaEvent Timer the same way, R/utils.hpp:85-92) */
@@ -262,6 +312,40 @@ int dlq_multi_create(const int* devices, int n_devices, const dlq_resnet18_weigh
 void dlq_multi_destroy(dlq_multi* m);
 int dlq_multi_forward_host(dlq_multi* m, const float* x_host, int N, float* logits_host);
 const char* dlq_multi_last_error_string(const dlq_multi* m);
+int dlq_multi_n_devices(const dlq_multi* m);
+/* uint8 HWC input (dlq_resnet18_set_preprocess on every replica, then 150 KB/image over the host link) */
+int dlq_multi_set_preprocess(dlq_multi* m, const float* mean3, const float* std3);
+int dlq_multi_forward_host_u8(dlq_multi* m, const uint8_t* x_hwc_host, int N, float* logits_host);
+/* asynchronous form: submit splits the batch and returns once every worker has its share queued; up to two batches per
+ * device are in flight.  dlq_multi_wait blocks until everything submitted so far has its logits in host memory. */
+int dlq_multi_submit_host(dlq_multi* m, const float* x_host, int N, float* logits_host);
+int dlq_multi_submit_host_u8(dlq_multi* m, const uint8_t* x_hwc_host, int N, float* logits_host);
+int dlq_multi_wait(dlq_multi* m);
+/* device-resident form: x_dev[g] / logits_dev[g] are DEVICE pointers on the g-th listed device (n_per_dev[g] fp32 NCHW
+ * images, n_per_dev[g] x 1000 logits); returns when every replica has finished. */
+int dlq_multi_forward_device(dlq_multi* m, const float* const* x_dev, const int* n_per_dev, float* const* logits_dev);
+
+/* ------------------------------------------------------------------ MNIST MLP forward
+ * The GPU counterpart of the reference's MLP forward - MN/v4.cu:255-302 forward_timed (matmul -> bias -> relu ->
+ * matmul -> bias -> softmax), MN/v5.cu:127-157 forward_pass_only, MN/v3.c:177-215 on the CPU - as INT8 (or E4M3) FC
+ * layers on the tensor-core GEMM core:
+ *     x_q   = quantise(x, s_x)                                                       QUANT_SPEC 2 / 6
+ *     h_q   = clamp(rne(fmaf(acc1, s_x s_w1[h] / s_h, b1[h] / s_h)), 0, 127)           bias + ReLU + requant fused (3)
+ *     logit = fmaf(acc2, s_h s_w2[o], b2[o])                                         QUANT_SPEC 5 (FC)
+ *     prob  = softmax(logit)                                                         K/softmax.cu form, no clamp
+ * w1 / w2 are HOST pointers in the reference's [in, out] layout (matmul_a_b(A[m,n], B[n,k]), MN/v3.c:125-134);
+ * s_x / s_h: activation scales (absmax / 127 of a calibration batch, or / 448 for fp8).  hid must be 64 or a
+ * multiple of 128 (MNIST: 784 -> 256 -> 10). */
+typedef struct dlq_mlp dlq_mlp;
+int dlq_mlp_create(dlq_ctx* ctx, const float* w1_in_hid, const float* b1, const float* w2_hid_out, const float* b2, int in,
+                   int hid, int out, float s_x, float s_h, int max_batch, int fp8, dlq_mlp** out_m);
+void dlq_mlp_destroy(dlq_mlp* m);
+/* x: fp32 [B, in] device; logits / probs: fp32 [B, out] device, either may be NULL */
+int dlq_mlp_forward(dlq_mlp* m, const float* x, int B, float* logits, float* probs);
+/* checkpoints of the LAST forward, DEVICE output: "input" = quantised x [B, in], "hidden" = h_q [B, hid] (bytes) */
+int dlq_mlp_checkpoint(dlq_mlp* m, const char* name, uint8_t* out);
+/* HOST: the per-row weight scales of layer 1 (hid values) or 2 (out values) */
+int dlq_mlp_weight_scales(const dlq_mlp* m, int layer, float* scale_host);
 
 #ifdef __cplusplus
 }

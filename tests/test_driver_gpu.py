@@ -135,7 +135,8 @@ def test_cpp_bench_driver(ctx):
     assert out.returncode == 0, out.stdout + out.stderr
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["n_gpus"] == 1 and d["batch"] == 8 and d["images_per_s"] > 0 and d["host_images_per_s"] > 0
-    assert 50 < d["latency_b1_us"] < 5000 and d["launches_per_forward"] == 23
+    assert 50 < d["latency_b1_us"] < 5000 and d["launches_per_forward"] == 20      # batch 8: shortcut convs fused
+    assert d["host_u8_pipelined_images_per_s"] > 0
     w = synth.make_weights(0)
     m = dlq_b200.ResNet18(ctx, w, synth.load_act_scales(0), 8)
     dl = torch.empty((8, 1000), dtype=torch.float32, device="cuda")
@@ -143,10 +144,15 @@ def test_cpp_bench_driver(ctx):
     ctx.sync()
     assert d["top1_image0"] == int(dl[0].argmax().item())
     m.close()
-    if torch.cuda.device_count() >= 2:
-        out = subprocess.run([exe, "--batch", "16", "--iters", "2", "--warmup", "1", "--gpus", "2"], capture_output=True,
+    # the batch-sharded driver: two replicas on device 0 (runs on a one-GPU box), and two devices when the box has them
+    lists = [["--devices", "0,0"]] + ([["--gpus", "2"]] if torch.cuda.device_count() >= 2 else [])
+    for extra in lists:
+        out = subprocess.run([exe, "--batch", "16", "--iters", "2", "--warmup", "1"] + extra, capture_output=True,
                              text=True, timeout=300)
         assert out.returncode == 0, out.stdout + out.stderr
         d2 = json.loads(out.stdout.strip().splitlines()[-1])
         assert d2["n_gpus"] == 2 and d2["batch_per_gpu"] == 8 and d2["top1_image0"] == d["top1_image0"]
+        for k in ("host_images_per_s", "host_pipelined_images_per_s", "host_u8_pipelined_images_per_s",
+                  "device_resident_images_per_s"):
+            assert d2[k] > 0, k
     assert subprocess.run([exe, "--bogus"], capture_output=True).returncode == 1

@@ -1,7 +1,12 @@
 """FP8 (E4M3) path, QUANT_SPEC section 6, through the C ABI vs the CPU oracle.
 The tensor core accumulates E4M3 products in FP32 in an unspecified order, the oracle in double: parity is by
-tolerance — raw accumulators within 2^-10 relative of the magnitude sum's scale, outputs within ONE E4M3 code on
->= 99.9 % of elements (identical on most), network logits within 1e-2 relative L2 (the figures QUANT_SPEC states)."""
+tolerance, and the bars below are QUANT_SPEC section 7's, word for word:
+  * one conv on identical inputs: raw accumulators within 1e-3 * max|acc|; outputs within ONE E4M3 code everywhere and
+    identical on >= 99.9 % of the elements;
+  * whole network (every layer's rounding differences feed the next): the first checkpoint (stem_pool) meets the
+    single-conv bar; later checkpoints are identical on >= 97 % and within one code on >= 99.9 % of the elements;
+    logits relative L2 error <= 1e-2 with identical arg-max;
+  * results do not depend on timing: one MMA issuer per accumulator, so repeated runs are bit-identical."""
 import numpy as np
 import pytest
 
@@ -99,8 +104,7 @@ def test_resnet18_fp8_network_vs_oracle():
         m.checkpoint(k, t)
         ctx.sync()
         d = _code_distance(t.cpu().numpy().view(np.uint8), ref[k])
-        # rounding differences propagate through the layers: the stated bar is on the first conv-level checkpoint
-        # exactly (<= 1 code, >= 99.9 % identical) and a widening allowance afterwards
+        # QUANT_SPEC 7, "whole network": single-conv bar on the first checkpoint, compounding allowance afterwards
         frac_same = (d == 0).mean()
         if k == "stem_pool":
             assert d.max() <= 1 and frac_same >= 0.999, (k, d.max(), frac_same)
@@ -111,4 +115,49 @@ def test_resnet18_fp8_network_vs_oracle():
     assert rel <= 1e-2, f"logits relative L2 error {rel}"
     assert np.array_equal(got.argmax(1), ref["logits"].argmax(1))
     m.close()
+    ctx.close()
+
+
+def test_fp8_results_do_not_depend_on_timing():
+    """FP32 accumulation does not commute, so the E4M3 kernels keep ONE MMA issuer per accumulator.  The
+    conv that used to split K between two issuers (one tile per item: 7x7, batch 1) and the whole network (plain and
+    CUDA-graph replay) give the same bytes on every run."""
+    import torch
+    import dlq_b200
+    from dlq_b200 import synth
+    ctx = dlq_b200.Context(0)
+    x = _codes((1, 512, 7, 7), 5, "fp8.det.x")
+    wq = _codes((512, 512, 3, 3), 5, "fp8.det.w", -64, 64)
+    alpha = np.full(512, 2.0 ** -6, np.float32)
+    beta = np.zeros(512, np.float32)
+    w = ctx.pack_conv_weights_e4m3(wq, 1, 1)
+    dx, da, db = torch.from_numpy(x).cuda(), torch.from_numpy(alpha).cuda(), torch.from_numpy(beta).cuda()
+    accs = []
+    for _ in range(6):
+        dacc = torch.empty((1, 512, 7, 7), dtype=torch.float32, device="cuda")
+        dy = torch.empty((1, 512, 7, 7), dtype=torch.uint8, device="cuda")
+        ctx.conv2d_fp8(dx, w, da, db, None, 0.0, True, dy, dacc)
+        ctx.sync()
+        accs.append(dacc.cpu().numpy().view(np.uint32).copy())
+    assert all(np.array_equal(accs[0], a) for a in accs[1:])
+    w.free()
+    wts = synth.make_weights(0)
+    s8 = orc.fp8_act_scales(synth.load_act_scales(0))
+    for n in (1, 3, 24):                 # fused-shortcut plans (n <= 16) and the large-batch plan
+        m = dlq_b200.ResNet18(ctx, wts, s8, n, fp8=True)
+        xin = torch.from_numpy(synth.make_input(1, n)).cuda()
+        outs = []
+        for _ in range(4):
+            dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+            m.forward(xin, dl)
+            ctx.sync()
+            outs.append(dl.cpu().numpy().view(np.uint32).copy())
+        dlg = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+        m.graph_capture(xin, dlg)
+        for _ in range(3):
+            m.graph_launch()
+            ctx.sync()
+            outs.append(dlg.cpu().numpy().view(np.uint32).copy())
+        assert all(np.array_equal(outs[0], o) for o in outs[1:]), n
+        m.close()
     ctx.close()

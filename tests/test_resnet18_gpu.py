@@ -40,10 +40,14 @@ def _forward(ctx, m, x):
     return out
 
 
-@pytest.mark.parametrize("n", [1, 3])
+@pytest.mark.parametrize("n", [1, 3, 17, 40])
 def test_network_matches_oracle(ctx, model256, n):
+    """n <= 16 runs the fused-shortcut plan (conv1 + 1x1/s2 in one launch, K-split issuers); n = 17 and 40 run the plan
+    the benchmark runs at batch 256 - separate 3x3/s2 and 1x1/s2 kernels reading parity-plane tensors - on DISTINCT
+    images, all six int8 checkpoints and the logits"""
     w = synth.make_weights(0)
     x = synth.make_input(7, n)
+    assert len({x[i].tobytes() for i in range(n)}) == n
     ref = orc.I8Model(w, synth.load_act_scales(0)).forward(x, checkpoints=True)
     got = _forward(ctx, model256, x)
     for k in CKPTS:
@@ -113,6 +117,114 @@ def test_forward_host_and_quantised_accuracy(ctx, model256):
     for i in range(2):
         cos = float(np.dot(f[i], lh.numpy()[i]) / (np.linalg.norm(f[i]) * np.linalg.norm(lh.numpy()[i])))
         assert cos > 0.98, cos
+
+
+def _tile(a, n):
+    return np.concatenate([a] * (n // a.shape[0] + 1), 0)[:n]
+
+
+def test_forward_host_chunked_batch256_matches_oracle(ctx, model256):
+    """the e2e headline path: dlq_resnet18_forward_host at N = 256 (64-image chunks, H2D overlapped with compute) on 32
+    distinct images (tiled) - every one of the 256 logit rows bit-equal to the oracle's"""
+    import torch
+    x32 = synth.make_input(11, 32)
+    ref = orc.I8Model(synth.make_weights(0), synth.load_act_scales(0)).forward(x32)["logits"]
+    xh = torch.from_numpy(_tile(x32, 256)).pin_memory()
+    lh = torch.zeros((256, 1000), dtype=torch.float32).pin_memory()
+    model256.forward_host(xh, lh)
+    assert np.array_equal(lh.numpy().view(np.uint32), _tile(ref, 256).view(np.uint32))
+    # a ragged batch (3 chunks of 64 + 8) through the same entry point
+    lh.zero_()
+    model256.forward_host(xh[:200], lh[:200])
+    assert np.array_equal(lh.numpy()[:200].view(np.uint32), _tile(ref, 200).view(np.uint32))
+    assert not lh.numpy()[200:].any()
+
+
+def test_forward_host_u8_chunked_batch256_matches_oracle(ctx, model256):
+    """dlq_resnet18_forward_host_u8 at N = 256 (128-image chunks): uint8 HWC images -> device-side table -> network, vs the
+    oracle run on the reference's numpy preprocessing of the same images (tools/preprocess_to_bin.py:24-33)"""
+    import torch
+    import dlq_b200
+    rng = np.random.default_rng(5)
+    u32 = rng.integers(0, 256, (32, 224, 224, 3), dtype=np.uint8)
+    mean = np.array(dlq_b200.ResNet18.IMAGENET_MEAN, dtype=np.float32)
+    std = np.array(dlq_b200.ResNet18.IMAGENET_STD, dtype=np.float32)
+    x = (u32.astype(np.float32) / np.float32(255.0) - mean) / std
+    x = np.ascontiguousarray(np.transpose(x, (0, 3, 1, 2)))
+    ref = orc.I8Model(synth.make_weights(0), synth.load_act_scales(0)).forward(x)["logits"]
+    model256.set_preprocess()
+    uh = torch.from_numpy(_tile(u32, 256)).pin_memory()
+    lh = torch.zeros((256, 1000), dtype=torch.float32).pin_memory()
+    model256.forward_host_u8(uh, lh)
+    assert np.array_equal(lh.numpy().view(np.uint32), _tile(ref, 256).view(np.uint32))
+
+
+def test_submit_wait_pipeline_matches_oracle(ctx, model256):
+    """pipelined host entry points (double-buffered staging, whole-batch forwards): five submits of different batches and
+    sizes with two in flight, fp32 and uint8 mixed - every result bit-equal to the oracle"""
+    import torch
+    import dlq_b200
+    w, sc = synth.make_weights(0), synth.load_act_scales(0)
+    orc_m = orc.I8Model(w, sc)
+    xs = [synth.make_input(20 + i, n) for i, n in enumerate((8, 5, 8))]
+    refs = [orc_m.forward(x)["logits"] for x in xs]
+    rng = np.random.default_rng(9)
+    u = rng.integers(0, 256, (6, 224, 224, 3), dtype=np.uint8)
+    mean = np.array(dlq_b200.ResNet18.IMAGENET_MEAN, dtype=np.float32)
+    std = np.array(dlq_b200.ResNet18.IMAGENET_STD, dtype=np.float32)
+    xu = np.ascontiguousarray(np.transpose((u.astype(np.float32) / np.float32(255.0) - mean) / std, (0, 3, 1, 2)))
+    ref_u = orc_m.forward(xu)["logits"]
+    model256.set_preprocess()
+    # batches of 256 / 160 / 256 images (tiled) so that the forwards take long enough to overlap the copies
+    sizes = (256, 160, 256)
+    hx = [torch.from_numpy(_tile(x, n)).pin_memory() for x, n in zip(xs, sizes)]
+    hu = torch.from_numpy(_tile(u, 192)).pin_memory()
+    hl = [torch.zeros((n, 1000), dtype=torch.float32).pin_memory() for n in sizes + (192, 256)]
+    model256.submit_host(hx[0], hl[0])
+    model256.submit_host(hx[1], hl[1])
+    model256.wait()
+    model256.submit_host_u8(hu, hl[3])
+    model256.wait()
+    model256.submit_host(hx[2], hl[2])
+    model256.wait()
+    model256.submit_host(hx[0], hl[4])
+    model256.wait()
+    model256.wait()
+    model256.wait()      # nothing outstanding: returns at once
+    for i, n in enumerate(sizes):
+        assert np.array_equal(hl[i].numpy().view(np.uint32), _tile(refs[i], n).view(np.uint32)), f"submit {i}"
+    assert np.array_equal(hl[3].numpy().view(np.uint32), _tile(ref_u, 192).view(np.uint32))
+    assert np.array_equal(hl[4].numpy().view(np.uint32), _tile(refs[0], 256).view(np.uint32))
+    # the synchronous entry point drains outstanding submits before it runs
+    model256.submit_host(hx[1], hl[1])
+    l2 = torch.zeros((8, 1000), dtype=torch.float32).pin_memory()
+    model256.forward_host(torch.from_numpy(xs[2]).pin_memory(), l2)
+    assert np.array_equal(l2.numpy().view(np.uint32), refs[2].view(np.uint32))
+
+
+def test_launch_count_and_span_stamps(ctx, model256):
+    """dlq_resnet18_launches_for_batch: 20 kernels when the shortcut convs are fused (N <= 16), 23 otherwise; the span
+    stamps of a forward are ordered like its launches"""
+    import torch
+    assert model256.launches == 23
+    assert model256.launches_for_batch(8) == 20 and model256.launches_for_batch(16) == 20
+    assert model256.launches_for_batch(17) == 23 and model256.launches_for_batch(256) == 23
+    x = torch.from_numpy(synth.make_input(0, 32)).cuda()
+    dl = torch.empty((32, 1000), dtype=torch.float32, device="cuda")
+    model256.enable_stamps(4)
+    for _ in range(3):
+        model256.forward(x, dl)
+    st = model256.read_stamps()
+    model256.enable_stamps(0)
+    assert st.shape == (3, 23, 2)
+    entry, exit_ = st[..., 0].astype(np.int64), st[..., 1].astype(np.int64)
+    assert (exit_ > entry).all() and (exit_ - entry < 5_000_000).all()
+    assert (exit_[:, -1] >= exit_[:, :-1].max(axis=1)).all(), "GAP+FC finishes last"
+    assert (entry[:, 1:] >= entry[:, :1]).all(), "the input quantisation enters first"
+    assert (entry[1:, 0] >= exit_[:-1, 21]).all(), "a forward starts after the previous one's last conv"
+    # stamps off again: results unchanged
+    model256.forward(x, dl)
+    ctx.sync()
 
 
 @pytest.mark.gpu
