@@ -73,7 +73,24 @@ __device__ __forceinline__ int dbg_flags(int f) {
 #endif
 }
 
+// Tile-level dependency on another conv launch of the same forward (instead of the grid-level griddepcontrol.wait): the
+// producer launch counts, per work-unit position index (super-tile, or super-tile pair), the epilogue warps that have
+// stored their part of it; a consumer item waits until the counters of every producer unit its patch (or residual rows)
+// touches have reached `target`.  See the "dependency flags" section of the kernel.
+struct ConvDep {
+  const unsigned int* done;   // producer's counters, one per (super-tile | pair) index
+  unsigned int target;        // producer n_tiles * epilogue warps * CTAs per unit
+  int unit;                   // producer positions per counter: super_stride * (pair ? 2 : 1)
+  int Pv, Wp, Wo, H;          // producer's virtual geometry: image pitch (rows), row pitch, valid width, valid rows
+  int s, lo, hi;              // producer rows my output row r needs: [r*s - lo, r*s + hi] (clipped to the image)
+};
+
 struct ConvKernelParams {
+  // dependency flags (all zero / null: grid-level dependencies through griddepcontrol.wait)
+  int n_deps;
+  ConvDep dep[2];
+  unsigned int* done;         // this launch's own counters (null: none kept)
+  unsigned int* dep_err;      // incremented when a dependency wait times out (~4 s): results are then invalid
   // virtual output space
   int Wp, Wo, Ho, Pv, N;
   int total_pos;          // N * Pv * Wp
@@ -531,6 +548,62 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dependency flags.  Consecutive conv launches of one forward are chained with programmatic dependent launch and, in
+// this mode, never call griddepcontrol.wait: CTAs of launch L+1 become resident as CTAs of L exit and start on whatever
+// items already have their inputs, so the tail of L (partial last wave, last epilogues, grid teardown) overlaps the
+// head of L+1.  No deadlock: L+1 is only scheduled once every CTA of L has started (launch_dependents at CTA entry),
+// and L's CTAs never wait for L+1.
+//   producer:  each epilogue warp, after its stores of an item:  __syncwarp; lane 0: __threadfence; atomicAdd(done[unit]).
+//   consumer:  warp 0, before the item's first patch load: all lanes poll (ld.acquire.gpu) the counters of the producer
+//              units its rows touch, then the elected lane fences (gpu scope + generic->async proxy) and issues the TMA.
+//   The counters are zeroed by the LAST kernel of the forward (GAP+FC, which waits for the whole last conv grid), so a
+//   forward always starts with zero counters and nothing of the previous forward can still increment them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// producer units [lo, hi] whose rows the consumer positions [g0, g1] need (lo > hi: none)
+__device__ __forceinline__ void dep_unit_range(const ConvKernelParams& p, const ConvDep& d, int g0, int g1, int& lo, int& hi) {
+  int va = g0 / p.Wp, vb = g1 / p.Wp;
+  int na = va / p.Pv, ra = va - na * p.Pv;
+  int nb = vb / p.Pv, rb = vb - nb * p.Pv;
+  if (ra >= p.Ho) { ++na; ra = 0; }                       // starts in the pad rows behind an image
+  if (nb >= p.N) { nb = p.N - 1; rb = p.Ho - 1; }
+  if (rb >= p.Ho) rb = p.Ho - 1;
+  if (na > nb || (na == nb && ra > rb)) { lo = 1; hi = 0; return; }
+  const int pra = max(0, ra * d.s - d.lo), prb = min(d.H - 1, rb * d.s + d.hi);
+  lo = ((na * d.Pv + pra) * d.Wp) / d.unit;
+  hi = ((nb * d.Pv + prb) * d.Wp + d.Wo - 1) / d.unit;
+}
+
+// whole warp: wait until every dependency of the positions [g0, g1] is satisfied
+__device__ __forceinline__ void wait_deps(const ConvKernelParams& p, int g0, int g1, int lane) {
+  for (int di = 0; di < p.n_deps; ++di) {
+    const ConvDep& d = p.dep[di];
+    int lo, hi;
+    dep_unit_range(p, d, g0, g1, lo, hi);
+    for (int u = lo + lane; u <= hi; u += 32) {
+      if (ld_acquire_gpu(d.done + u) >= d.target) continue;
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+      unsigned int spins = 0;
+      while (ld_acquire_gpu(d.done + u) < d.target) {
+        if ((++spins & 1023u) == 0) {                     // a lost producer must not hang the GPU: give up after ~4 s
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+          if (t1 - t0 > 4000000000ULL) { atomicAdd(p.dep_err, 1u); break; }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha, beta: 2*OC f32]
 //   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
@@ -573,6 +646,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   uint64_t* acc_empty = acc_full + p.acc_stages;
   uint64_t* k_first = acc_empty + p.acc_stages;       // K-split handshake, one per accumulator stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_first + p.acc_stages);
+  volatile uint32_t* s_dep_seq = tmem_slot + 1;       // items of this CTA whose dependencies the patch producer has verified
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_epi_warps = (blockDim.x >> 5) - 4;
@@ -606,6 +680,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     fence_mbar_init();
     tma_prefetch_desc(&tm0);
     tma_prefetch_desc(&tmw);
+    *s_dep_seq = 0u;
   }
   if (warp == 1) {
     if (TWO) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
@@ -622,14 +697,28 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 
   if (warp == 0) {
     // ===================================================================== A (activation patch) producer
-    if (elect_one()) {
-      uint32_t as = 0, aph = 0;
-      long long t_wait = 0;
-      const long long t_begin = dbg_clock();
-      pdl_wait();   // activations come from the previous kernel(s); everything above (and the weight loads) does not
-      for (int it = gid; it < p.n_items; it += G) {
-        const int sp = it / p.n_tiles;
-        const int st = TWO ? 2 * sp + rank : sp;
+    // One elected lane issues the loads; with dependency flags the whole warp first polls the producer counters of the
+    // item (lanes in parallel), so the other lanes walk the item loop too.
+    const bool leader = elect_one();
+    uint32_t as = 0, aph = 0;
+    long long t_wait = 0;
+    const long long t_begin = dbg_clock();
+    if (p.n_deps == 0 && leader) pdl_wait();   // grid-level dependency: activations come from the previous kernel(s);
+                                                // everything above (and the weight loads) does not
+    uint32_t seq = 0;
+    for (int it = gid; it < p.n_items; it += G) {
+      const int sp = it / p.n_tiles;
+      const int st = TWO ? 2 * sp + rank : sp;
+      if (p.n_deps) {
+        const int g0 = st * p.super_stride;
+        wait_deps(p, g0, min(g0 + p.super_stride, p.total_pos) - 1, lane);
+      }
+      if (leader) {
+        if (p.n_deps) {
+          __threadfence();           // the other lanes' acquires -> (syncwarp) -> this lane, at gpu scope
+          fence_proxy_async_all();   // producer's generic-proxy stores before this thread's async-proxy (TMA) reads
+          *s_dep_seq = ++seq;        // the epilogue warps may now prefetch this item's residual rows
+        }
         const int v0 = (st * p.super_stride) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
           const long long tw = dbg_clock();
@@ -652,10 +741,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           if (++as == static_cast<uint32_t>(p.a_stages)) { as = 0; aph ^= 1u; }
         }
       }
-      if (p.dbg_times) {
-        long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
-        d[6] = dbg_clock() - t_begin; d[7] = t_wait;
-      }
+    }
+    if (p.dbg_times && leader) {
+      long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
+      d[6] = dbg_clock() - t_begin; d[7] = t_wait;
     }
   } else if (warp == 2) {
     // ===================================================================== B (weight step) producer
@@ -782,8 +871,20 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       if (p.fused) { s_alpha2[i] = p.alpha2[i]; s_beta2[i] = p.beta2[i]; }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
-    pdl_wait();     // the residual is an earlier kernel's output, and our stores must not race its readers
-    if (has_res && gid < p.n_items && n_pairs > 0) prefetch_pair(gid, 0);
+    // grid-level mode: the residual is an earlier kernel's output, and our stores must not race its readers.  Flag mode:
+    // the residual rows of item k are read only once the patch producer has verified item k's dependencies (it
+    // publishes the count of verified items in s_dep_seq); stores need no wait - every tensor of a forward has its own
+    // buffer, and the previous forward's readers finished before this forward began.
+    const bool flag_mode = p.n_deps != 0;
+    if (!flag_mode) pdl_wait();
+    uint32_t eseq = 0;      // items of this CTA whose residual has been requested
+    auto wait_dep_seq = [&](uint32_t want) {
+      if (flag_mode) {
+        while (*s_dep_seq < want) { }
+        __threadfence();
+      }
+    };
+    if (has_res && gid < p.n_items && n_pairs > 0) { wait_dep_seq(++eseq); prefetch_pair(gid, 0); }
     for (int it = gid; it < p.n_items; it += G) {
       const int sp = it / p.n_tiles;
       const int nt = it - sp * p.n_tiles;
@@ -837,7 +938,14 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
 #undef DLQ_EPI
         if (has_res) {
           if (pi + 1 < n_pairs) prefetch_pair(it, pi + 1);
-          else if (it + G < p.n_items) prefetch_pair(it + G, 0);
+          else if (it + G < p.n_items) { wait_dep_seq(++eseq); prefetch_pair(it + G, 0); }
+        }
+      }
+      if (p.done) {          // this warp's part of the item is stored: count it for the consumers (see "dependency flags")
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(p.done + sp, 1u);
         }
       }
       if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back

@@ -336,7 +336,11 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const long long total_pos = static_cast<long long>(in.N) * p.Pv * p.Wp;
   DLQ_ARG(ctx, total_pos + 4LL * MT * kTileM < (1LL << 31), "batch too large for 32-bit position arithmetic");
   p.total_pos = static_cast<int>(total_pos);
-  p.num_super = static_cast<int>((total_pos + p.super_stride - 1) / p.super_stride);
+  // super-tiles up to the one holding the last VALID position (last image, last row, last column): the pad rows behind
+  // the last image would only make items whose every position is garbage (and, with dependency flags, units that no
+  // consumer ever waits for)
+  const long long last_valid = (static_cast<long long>(in.N - 1) * p.Pv + (p.Ho - 1)) * p.Wp + (p.Wo - 1);
+  p.num_super = static_cast<int>(last_valid / p.super_stride) + 1;
   p.n_items = ((p.num_super + ncta - 1) / ncta) * n_tiles;
   // epilogue position decode by multiply-high instead of division: exact while positions < 2^24 and divisors <= 256
   // (floor(2^32/d)+1; the kernel falls back to hardware division when the magics are 0)
@@ -513,6 +517,27 @@ int configure_conv_kernels(dlq_ctx* ctx) {
   DLQ_CUDA(ctx, (configure_t<64, true, true>(ctx)));
   DLQ_CUDA(ctx, (configure_t<128, true, true>(ctx)));
   return DLQ_OK;
+}
+
+// ---- dependency flags (conv_kernel.cuh "dependency flags")
+int conv_flag_units(const ConvLaunch& L) { return L.p.n_items / L.p.n_tiles; }
+void conv_set_flags(ConvLaunch* L, unsigned int* done, unsigned int* dep_err) {
+  L->p.done = done;
+  L->p.dep_err = dep_err;
+}
+void conv_add_dep(ConvLaunch* consumer, const ConvLaunch& producer, int s, int lo, int hi) {
+  ConvKernelParams& c = consumer->p;
+  const ConvKernelParams& q = producer.p;
+  if (c.n_deps >= 2 || !q.done) return;
+  for (int i = 0; i < c.n_deps; ++i)
+    if (c.dep[i].done == q.done && c.dep[i].s == s && c.dep[i].lo >= lo && c.dep[i].hi >= hi) return;   // already covered
+  ConvDep& d = c.dep[c.n_deps++];
+  const int ncta = q.two ? 2 : 1;
+  d.done = q.done;
+  d.target = static_cast<unsigned int>(q.n_tiles) * 8u * static_cast<unsigned int>(ncta);
+  d.unit = q.super_stride * ncta;
+  d.Pv = q.Pv; d.Wp = q.Wp; d.Wo = q.Wo; d.H = q.Ho;
+  d.s = s; d.lo = lo; d.hi = hi;
 }
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {

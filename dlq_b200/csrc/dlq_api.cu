@@ -485,6 +485,12 @@ struct dlq_resnet18 {
   int fifo[2] = {0, 0};       // outstanding submits, oldest first
   int n_outstanding = 0;
   cudaStream_t d2h_stream = nullptr;
+  // dependency flags between the conv launches of a forward (conv_kernel.cuh "dependency flags"): per-unit completion
+  // counters of every conv, one buffer sized for max_batch; [n_flags] is the timeout counter
+  bool tile_flags = true;
+  unsigned int* d_flags = nullptr;
+  int n_flags = 0;
+  bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
   // span stamps: ring of [forward][launch][2] globaltimer values (dlq_resnet18_enable_stamps)
   unsigned long long* d_stamps = nullptr;
   int stamp_ring = 0;
@@ -493,6 +499,7 @@ struct dlq_resnet18 {
     int N = 0;
     ConvLaunch L[DLQ_NUM_CONVS];
     bool fused[8] = {false};    // block b's shortcut conv runs inside L[conv1 of b]
+    int flag_units = 0;         // dependency counters this plan uses
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
@@ -582,6 +589,44 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
     if (rc != DLQ_OK) return rc;
     cur = o;
     s_cur = S[act_out(b)];
+  }
+  // ---- dependency flags: every block conv keeps per-unit completion counters; every conv behind the first one waits
+  // for the units of its producers instead of for their whole grids.  (The stem, the max-pool behind it and the first
+  // block's conv1 keep the grid-level dependency: their producers are not conv launches.)
+  int units = 0;
+  auto keep = [&](ConvLaunch& L) {
+    const int n = conv_flag_units(L);
+    if (m->d_flags && m->tile_flags && units + n <= m->n_flags) conv_set_flags(&L, m->d_flags + units, m->d_flags + m->n_flags);
+    units += n;
+  };
+  for (int b = 0; b < 8; ++b) {
+    keep(P->L[1 + 3 * b]);
+    if (kBlocks[b].down && !P->fused[b]) keep(P->L[3 + 3 * b]);
+    keep(P->L[2 + 3 * b]);
+  }
+  P->flag_units = units;
+  if (m->d_flags && m->tile_flags && units <= m->n_flags) {
+    const ConvLaunch* prev_out = nullptr;      // the conv that produced this block's input (null: the max-pool)
+    for (int b = 0; b < 8; ++b) {
+      ConvLaunch& c1 = P->L[1 + 3 * b];
+      ConvLaunch& c2 = P->L[2 + 3 * b];
+      const int s = kBlocks[b].stride;
+      if (prev_out) conv_add_dep(&c1, *prev_out, s, 1, 1);                   // 3x3: input rows r*s - 1 .. r*s + 1
+      const ConvLaunch* ds = nullptr;
+      if (kBlocks[b].down) {
+        if (P->fused[b]) {
+          ds = &c1;                                                          // the shortcut's rows are conv1's units
+        } else {
+          ConvLaunch& d = P->L[3 + 3 * b];
+          if (prev_out) conv_add_dep(&d, *prev_out, s, 0, 0);               // 1x1/s2: input row 2r
+          ds = &d;
+        }
+      }
+      conv_add_dep(&c2, c1, 1, 1, 1);
+      if (ds) conv_add_dep(&c2, *ds, 1, 0, 0);                              // residual rows r
+      else if (prev_out) conv_add_dep(&c2, *prev_out, 1, 0, 0);            // identity skip = the block input
+      prev_out = &c2;
+    }
   }
   return DLQ_OK;
 }
@@ -733,10 +778,21 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
     m->d_lut = static_cast<uint8_t*>(p);
   }
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  // plan the full batch now so the first forward does no host planning
+  // plan the full batch now so the first forward does no host planning; a first pass sizes the dependency counters
   std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
   rc = build_plan(m.get(), N, P.get());
   if (rc != DLQ_OK) return rc;
+  {
+    m->n_flags = P->flag_units;
+    void* p = nullptr;
+    DLQ_CUDA(ctx, cudaMalloc(&p, (static_cast<size_t>(m->n_flags) + 1) * sizeof(unsigned int)));
+    m->allocs.push_back(p);
+    m->d_flags = static_cast<unsigned int*>(p);
+    DLQ_CUDA(ctx, cudaMemsetAsync(p, 0, (static_cast<size_t>(m->n_flags) + 1) * sizeof(unsigned int), ctx->stream));
+    DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = build_plan(m.get(), N, P.get());
+    if (rc != DLQ_OK) return rc;
+  }
   m->plans[N] = std::move(P);
   *out = m.release();
   return DLQ_OK;
@@ -773,6 +829,12 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   }
   const dlq_resnet18::Plan& P = *it->second;
   const float* S = m->act_scale;
+  // dependency counters: zero at the start of every forward - the last kernel of the previous one cleared them; only a
+  // forward that failed half-way leaves them dirty
+  const bool flags_on = m->tile_flags && m->d_flags && P.flag_units <= m->n_flags;
+  if (m->flags_dirty && m->d_flags)
+    DLQ_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, static_cast<size_t>(m->n_flags) * sizeof(unsigned int), ctx->stream));
+  m->flags_dirty = flags_on;
   int e = 0;
   auto mark = [&]() -> int {
     if (ev) DLQ_CUDA(ctx, cudaEventRecord(ev[e++], ctx->stream));
@@ -822,12 +884,15 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   }
   const Act last = with_n(m->a_out[7], N);
   const float s_over_hw = static_cast<float>(static_cast<double>(S[act_out(7)]) / static_cast<double>(last.H * last.W));
+  unsigned int* zero = flags_on ? m->d_flags : nullptr;
+  const int n_zero = flags_on ? P.flag_units : 0;
   rc = m->fp8 ? gap_fc_act_e4m3(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000,
-                                m->d_gap_q, logits)
+                                m->d_gap_q, logits, zero, n_zero)
               : gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
-                           logits, stamp());
+                           logits, stamp(), zero, n_zero);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
+  m->flags_dirty = false;
   m->last_N = N;
   return DLQ_OK;
 }
@@ -835,6 +900,40 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
 int dlq_resnet18_forward(dlq_resnet18* m, const float* x, int N, float* logits) {
   if (!m) return DLQ_ERR_ARG;
   return forward_impl(m, x, N, logits, nullptr);
+}
+
+/* Options (measurement / A-B comparisons).  "tile_flags" = 1 (default): consecutive conv launches depend on each other tile
+ * by tile through completion counters, so the tail of one overlaps the head of the next; 0: every launch waits for the
+ * whole previous grid (griddepcontrol.wait).  Both give bit-identical results.  Synchronises and drops the cached plans. */
+int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, key != nullptr, "null key");
+  DLQ_ARG(ctx, std::string(key) == "tile_flags", "unknown option (tile_flags)");
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  m->tile_flags = value != 0;
+  m->plans.clear();
+  if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
+  if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
+  if (m->d_flags) {
+    DLQ_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, (static_cast<size_t>(m->n_flags) + 1) * sizeof(unsigned int), ctx->stream));
+    DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  m->flags_dirty = false;
+  return DLQ_OK;
+}
+/* dependency waits that timed out since creation (a lost producer; must stay 0).  Synchronises. */
+int dlq_resnet18_dep_timeouts(dlq_resnet18* m, unsigned int* count) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, count != nullptr, "null pointer");
+  *count = 0;
+  if (!m->d_flags) return DLQ_OK;
+  DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
+  DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DLQ_CUDA(ctx, cudaMemcpy(count, m->d_flags + m->n_flags, sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return DLQ_OK;
 }
 
 /* Span stamps: with a ring of `ring_forwards` entries enabled, every kernel of a forward records the globaltimer (ns) of

@@ -127,6 +127,11 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
               const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L,
               const SecondConv* second = nullptr);
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L);
+// dependency flags between the conv launches of one forward (conv_kernel.cuh "dependency flags"):
+int conv_flag_units(const ConvLaunch& L);                                          // counters the launch needs
+void conv_set_flags(ConvLaunch* L, unsigned int* done, unsigned int* dep_err);     // keep per-unit completion counters
+// `consumer` waits, per item, for the units of `producer` holding rows [r*s - lo, r*s + hi] of its output rows r
+void conv_add_dep(ConvLaunch* consumer, const ConvLaunch& producer, int s, int lo, int hi);
 void conv_out_dims(const dlq_conv_weights* w, int H, int W, int* OH, int* OW);
 
 // elementwise.cu (all enqueue on ctx->stream)
@@ -139,12 +144,15 @@ int quantize_input_s2d(dlq_ctx* ctx, const float* x, int N, int H, int W, float 
 int preprocess_u8_s2d(dlq_ctx* ctx, const uint8_t* x_hwc, int N, int H, int W, const uint8_t* lut_dev, const Act& a,
                       unsigned long long* stamp = nullptr);
 int maxpool_act(dlq_ctx* ctx, const Act& in, const Act& out, unsigned long long* stamp = nullptr);
+// zero / n_zero: the forward's dependency counters, cleared by this last kernel of the forward once the last conv grid
+// has completed (conv_kernel.cuh "dependency flags")
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
                const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits,
-               unsigned long long* stamp = nullptr);
+               unsigned long long* stamp = nullptr, unsigned int* zero = nullptr, int n_zero = 0);
 
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits);
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits,
+                    unsigned int* zero = nullptr, int n_zero = 0);
 
 // dlq_api.cu: per-row symmetric quantisation of a [rows, K] fp32 matrix (QUANT_SPEC 1 / 6), host
 void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s);

@@ -348,9 +348,11 @@ __global__ void dequantize_e4m3_f32_kernel(const uint8_t* __restrict__ q, size_t
 __global__ void __launch_bounds__(512)
 gap_fc_e4m3_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
                    float inv_gap_scale, const int8_t* __restrict__ fc_wT, const float* __restrict__ fc_scale,
-                   const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits) {
+                   const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits,
+                   unsigned int* __restrict__ zero, int n_zero) {
   extern __shared__ float gq_s[];     // [C] dequantised (unit-scale) gap values
   const int n = blockIdx.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero[i] = 0u;   // (as gap_fc_kernel)
   const uint8_t* img = reinterpret_cast<const uint8_t*>(in) + (static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR)) * W * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float s = 0.f;
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(512)
 gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
               float inv_gap_scale, const int8_t* __restrict__ fc_w, const float* __restrict__ fc_scale,
               const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits,
-              unsigned long long* stamp) {
+              unsigned long long* stamp, unsigned int* __restrict__ zero, int n_zero) {
   extern __shared__ int4 smem_gap[];
   stamp_entry(stamp);
   int32_t* part_sum = reinterpret_cast<int32_t*>(smem_gap);                                 // [imgs][parts][C]
@@ -611,6 +613,9 @@ gap_fc_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR,
   const int nimg = min(kGapImgs, N - n0);
   const int HW = H * W;
   pdl_wait();
+  // the last conv grid has completed, hence every dependency counter of this forward is final: clear them for the next
+  for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * gridDim.y * blockDim.x)
+    zero[i] = 0u;
   {
     // phase 1a: thread = (image, pixel partition, 16-channel group); 16-byte loads, all independent
     const int im = threadIdx.x >> 7, part = (threadIdx.x >> 5) & 3, lane = threadIdx.x & 31;
@@ -888,21 +893,25 @@ int configure_elementwise_kernels(dlq_ctx* ctx) {
   return DLQ_OK;
 }
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits) {
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned int* zero,
+                    int n_zero) {
   DLQ_ARG(ctx, in.C % 16 == 0 && O <= 1024, "gap/fc geometry");
   gap_fc_e4m3_kernel<<<in.N, 512, in.C * sizeof(float), ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
-                                                                     inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits);
+                                                                     inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits,
+                                                                     zero, n_zero);
   DLQ_CUDA(ctx, cudaGetLastError());
   return DLQ_OK;
 }
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned long long* stamp) {
+               const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned long long* stamp,
+               unsigned int* zero, int n_zero) {
   DLQ_ARG(ctx, in.C % 512 == 0 || in.C % 16 == 0, "gap channels");
   DLQ_ARG(ctx, in.C % 512 == 0, "fused GAP+FC expects a multiple of 512 channels");
   const int blocks = (in.N + kGapImgs - 1) / kGapImgs;
   const size_t gap_smem = static_cast<size_t>(kGapImgs) * kGapParts * in.C * 4 + static_cast<size_t>(kGapImgs) * in.C;
   DLQ_CUDA(ctx, launch_pdl(ctx, gap_fc_kernel, dim3(blocks, logits ? kGapOSplit : 1), dim3(512), gap_smem, static_cast<const int8_t*>(in.ptr),
-                           in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits, stamp));
+                           in.N, in.H, in.W, in.C, in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits, stamp, zero,
+                           n_zero));
   return DLQ_OK;
 }
 

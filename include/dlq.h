@@ -247,6 +247,13 @@ int dlq_resnet18_launches(const dlq_resnet18* m);
 /* kernels a forward of batch N really launches: 23, or 20 when the three 1x1 shortcut convs ride on conv1's launch
  * (N <= 16) */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
+/* Option "tile_flags" (default 1): consecutive conv launches of a forward depend on each other tile by tile, through
+ * completion counters in device memory, instead of grid by grid (griddepcontrol.wait): CTAs of launch L+1 start on the
+ * items whose inputs are ready while launch L drains.  0 restores grid-level dependencies (A/B measurements); results
+ * are bit-identical either way.  Synchronises. */
+int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value);
+/* dependency waits that ran into the 4 s safety timeout since creation (must be 0).  Synchronises. */
+int dlq_resnet18_dep_timeouts(dlq_resnet18* m, unsigned int* count);
 /* Span stamps (measurement): with a ring of `ring_forwards` entries, every kernel of a forward records the globaltimer
  * (ns) of its first block entry and last block exit - its span INSIDE a running sequence of forwards, overlap with its
  * neighbours included, which an event between launches cannot see.  dlq_resnet18_read_stamps synchronises, copies

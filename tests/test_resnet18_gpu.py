@@ -227,6 +227,48 @@ def test_launch_count_and_span_stamps(ctx, model256):
     ctx.sync()
 
 
+@pytest.mark.parametrize("n", [1, 9, 24, 256])
+def test_tile_dependency_flags_equal_grid_dependencies(ctx, n):
+    """tile-level dependency flags between the conv launches (the default) vs grid-level griddepcontrol.wait: identical
+    checkpoints and logits; repeated forwards and CUDA-graph replays never change a bit (a race between a consumer
+    tile and its producer would); no dependency wait ever times out"""
+    import torch
+    import dlq_b200
+    m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    x = _tile(synth.make_input(13, min(n, 32)), n)
+    want = _forward(ctx, m, x)
+    if n <= 32:
+        ref = orc.I8Model(synth.make_weights(0), synth.load_act_scales(0)).forward(x[:min(n, 32)], checkpoints=True)
+        for k in CKPTS:
+            assert np.array_equal(want[k], ref[k]), k
+    m.set_option("tile_flags", 0)
+    got = _forward(ctx, m, x)
+    for k in list(CKPTS) + ["logits"]:
+        assert np.array_equal(got[k], want[k]), k
+    m.set_option("tile_flags", 1)
+    dx = torch.from_numpy(x).cuda()
+    dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    for rep in range(40 if n < 256 else 15):
+        dl.fill_(7.0)
+        m.forward(dx, dl)
+        if rep % 5 == 4:
+            ctx.sync()
+            assert np.array_equal(dl.cpu().numpy().view(np.uint32), want["logits"].view(np.uint32)), rep
+    m.graph_capture(dx, dl)
+    for rep in range(20):
+        m.graph_launch()
+    ctx.sync()
+    assert np.array_equal(dl.cpu().numpy().view(np.uint32), want["logits"].view(np.uint32))
+    # a different batch size on the same model (other plan, same counters)
+    if n >= 9:
+        got2 = _forward(ctx, m, x[:5])
+        assert np.array_equal(got2["logits"].view(np.uint32), want["logits"][:5].view(np.uint32))
+        got3 = _forward(ctx, m, x)
+        assert np.array_equal(got3["layer3"], want["layer3"])
+    assert m.dep_timeouts == 0
+    m.close()
+
+
 @pytest.mark.gpu
 def test_u8_input_path_equals_reference_preprocessing():
     """uint8 HWC images through the device-side table == the reference's numpy preprocessing
