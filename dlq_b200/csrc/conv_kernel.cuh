@@ -317,6 +317,75 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
 
 
 // ------------------------------------------------------------------------------------------------
+// Dependency flags.  Consecutive conv launches of one forward are chained with programmatic dependent launch and, in
+// this mode, never call griddepcontrol.wait: CTAs of launch L+1 become resident as CTAs of L exit and start on whatever
+// items already have their inputs, so the tail of L (partial last wave, last epilogues, grid teardown) overlaps the
+// head of L+1.  No deadlock: L+1 is only scheduled once every CTA of L has started (launch_dependents at CTA entry),
+// and L's CTAs never wait for L+1.
+//   producer:  each epilogue warp, after its stores of an item, counts itself in shared memory; a signaller lane fences
+//              and adds the item's 8 arrivals to done[unit] (see "Producer side" below).
+//   consumer:  warp 0, before the item's first patch load: all lanes poll (ld.acquire.gpu) the counters of the producer
+//              units its rows touch, then the elected lane fences (gpu scope + generic->async proxy) and issues the TMA.
+//   The counters are zeroed by the LAST kernel of the forward (GAP+FC, which waits for the whole last conv grid), so a
+//   forward always starts with zero counters and nothing of the previous forward can still increment them.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// producer units [lo, hi] whose rows the consumer positions [g0, g1] need (lo > hi: none)
+__device__ __forceinline__ void dep_unit_range(const ConvKernelParams& p, const ConvDep& d, int g0, int g1, int& lo, int& hi) {
+  int va = g0 / p.Wp, vb = g1 / p.Wp;
+  int na = va / p.Pv, ra = va - na * p.Pv;
+  int nb = vb / p.Pv, rb = vb - nb * p.Pv;
+  if (ra >= p.Ho) { ++na; ra = 0; }                       // starts in the pad rows behind an image
+  if (nb >= p.N) { nb = p.N - 1; rb = p.Ho - 1; }
+  if (rb >= p.Ho) rb = p.Ho - 1;
+  if (na > nb || (na == nb && ra > rb)) { lo = 1; hi = 0; return; }
+  const int pra = max(0, ra * d.s - d.lo), prb = min(d.H - 1, rb * d.s + d.hi);
+  lo = ((na * d.Pv + pra) * d.Wp) / d.unit;
+  hi = ((nb * d.Pv + prb) * d.Wp + d.Wo - 1) / d.unit;
+}
+
+// whole warp: wait until every dependency of the positions [g0, g1] is satisfied.  The counters of all dependencies are
+// polled by different lanes at once (one L2 round trip when everything is ready).
+__device__ __forceinline__ void wait_deps(const ConvKernelParams& p, int g0, int g1, int lane) {
+  int lo0 = 1, hi0 = 0, lo1 = 1, hi1 = 0;
+  dep_unit_range(p, p.dep[0], g0, g1, lo0, hi0);
+  if (p.n_deps > 1) dep_unit_range(p, p.dep[1], g0, g1, lo1, hi1);
+  const int c0 = max(hi0 - lo0 + 1, 0), c1 = max(hi1 - lo1 + 1, 0);
+  for (int i = lane; i < c0 + c1; i += 32) {
+    const bool second = i >= c0;
+    const unsigned int* ctr = second ? p.dep[1].done + lo1 + (i - c0) : p.dep[0].done + lo0 + i;
+    const unsigned int target = second ? p.dep[1].target : p.dep[0].target;
+    if (ld_acquire_gpu(ctr) >= target) continue;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    unsigned int spins = 0;
+    while (ld_acquire_gpu(ctr) < target) {
+      if ((++spins & 1023u) == 0) {                     // a lost producer must not hang the GPU: give up after ~4 s
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 4000000000ULL) { atomicAdd(p.dep_err, 1u); break; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+// Producer side.  The gpu-scope fence in front of the counter update has to wait for outstanding stores (of the whole
+// SM, in practice: ~0.8 us per item when issued by an epilogue warp, measured), so the epilogue warps do not issue it:
+// each warp, after its stores of an item, adds 1 to a SHARED-memory count (red.release.cta, ring of 4 slots, counts are
+// cumulative so nothing is ever reset), and a spare lane of the weight-producer warp - the "signaller" - waits for the
+// eight arrivals of item k (acquire.cta), fences at gpu scope (cumulative: it orders the epilogue warps' stores it has
+// observed through the shared count) and publishes the item with ONE atomicAdd of 8 on the global counter.  Epilogue
+// warps are at most two items apart (two TMEM stages), so an arrival for item k+4 can only come after item k is complete.
+constexpr int kStoredSlots = 4;
+
+// ------------------------------------------------------------------------------------------------
 // Epilogue (8 warps).  A "unit" is (M tile, 64-channel block): per unit a warp turns its 32 accumulator rows x 64
 // int32 into 32 x 64 int8.  Units are processed in PAIRS so that two tcgen05.ld are in flight and - when the two
 // units are the same channel block of two tiles - every alpha/beta shared-memory read serves both.
@@ -548,62 +617,6 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Dependency flags.  Consecutive conv launches of one forward are chained with programmatic dependent launch and, in
-// this mode, never call griddepcontrol.wait: CTAs of launch L+1 become resident as CTAs of L exit and start on whatever
-// items already have their inputs, so the tail of L (partial last wave, last epilogues, grid teardown) overlaps the
-// head of L+1.  No deadlock: L+1 is only scheduled once every CTA of L has started (launch_dependents at CTA entry),
-// and L's CTAs never wait for L+1.
-//   producer:  each epilogue warp, after its stores of an item:  __syncwarp; lane 0: __threadfence; atomicAdd(done[unit]).
-//   consumer:  warp 0, before the item's first patch load: all lanes poll (ld.acquire.gpu) the counters of the producer
-//              units its rows touch, then the elected lane fences (gpu scope + generic->async proxy) and issues the TMA.
-//   The counters are zeroed by the LAST kernel of the forward (GAP+FC, which waits for the whole last conv grid), so a
-//   forward always starts with zero counters and nothing of the previous forward can still increment them.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// producer units [lo, hi] whose rows the consumer positions [g0, g1] need (lo > hi: none)
-__device__ __forceinline__ void dep_unit_range(const ConvKernelParams& p, const ConvDep& d, int g0, int g1, int& lo, int& hi) {
-  int va = g0 / p.Wp, vb = g1 / p.Wp;
-  int na = va / p.Pv, ra = va - na * p.Pv;
-  int nb = vb / p.Pv, rb = vb - nb * p.Pv;
-  if (ra >= p.Ho) { ++na; ra = 0; }                       // starts in the pad rows behind an image
-  if (nb >= p.N) { nb = p.N - 1; rb = p.Ho - 1; }
-  if (rb >= p.Ho) rb = p.Ho - 1;
-  if (na > nb || (na == nb && ra > rb)) { lo = 1; hi = 0; return; }
-  const int pra = max(0, ra * d.s - d.lo), prb = min(d.H - 1, rb * d.s + d.hi);
-  lo = ((na * d.Pv + pra) * d.Wp) / d.unit;
-  hi = ((nb * d.Pv + prb) * d.Wp + d.Wo - 1) / d.unit;
-}
-
-// whole warp: wait until every dependency of the positions [g0, g1] is satisfied
-__device__ __forceinline__ void wait_deps(const ConvKernelParams& p, int g0, int g1, int lane) {
-  for (int di = 0; di < p.n_deps; ++di) {
-    const ConvDep& d = p.dep[di];
-    int lo, hi;
-    dep_unit_range(p, d, g0, g1, lo, hi);
-    for (int u = lo + lane; u <= hi; u += 32) {
-      if (ld_acquire_gpu(d.done + u) >= d.target) continue;
-      unsigned long long t0;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-      unsigned int spins = 0;
-      while (ld_acquire_gpu(d.done + u) < d.target) {
-        if ((++spins & 1023u) == 0) {                     // a lost producer must not hang the GPU: give up after ~4 s
-          unsigned long long t1;
-          asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-          if (t1 - t0 > 4000000000ULL) { atomicAdd(p.dep_err, 1u); break; }
-        }
-      }
-    }
-  }
-  __syncwarp();
-}
-
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha, beta: 2*OC f32]
 //   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
@@ -647,6 +660,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
   uint64_t* k_first = acc_empty + p.acc_stages;       // K-split handshake, one per accumulator stage
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(k_first + p.acc_stages);
   volatile uint32_t* s_dep_seq = tmem_slot + 1;       // items of this CTA whose dependencies the patch producer has verified
+  uint32_t* s_stored = tmem_slot + 2;                 // [kStoredSlots] cumulative epilogue-warp arrivals per item slot
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_epi_warps = (blockDim.x >> 5) - 4;
@@ -681,6 +695,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     tma_prefetch_desc(&tm0);
     tma_prefetch_desc(&tmw);
     *s_dep_seq = 0u;
+    for (int i = 0; i < kStoredSlots; ++i) s_stored[i] = 0u;
   }
   if (warp == 1) {
     if (TWO) { tmem_alloc_pair(tmem_slot, tmem_cols); tmem_relinquish_pair(); }
@@ -715,9 +730,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       }
       if (leader) {
         if (p.n_deps) {
-          __threadfence();           // the other lanes' acquires -> (syncwarp) -> this lane, at gpu scope
+          // (the polling lanes' acquires reach this lane through wait_deps' __syncwarp: causality order is transitive)
           fence_proxy_async_all();   // producer's generic-proxy stores before this thread's async-proxy (TMA) reads
-          *s_dep_seq = ++seq;        // the epilogue warps may now prefetch this item's residual rows
+          ++seq;                     // the epilogue warps may now prefetch this item's residual rows
+          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))), "r"(seq) : "memory");
         }
         const int v0 = (st * p.super_stride) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
@@ -750,7 +766,23 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     // ===================================================================== B (weight step) producer
     // weight image rows: [(n-tile * n_steps + step) * n_tile + channel], ROWB bytes each (pre-swizzled); a CTA of a
     // pair loads its half of the channels
-    if (elect_one()) {
+    const bool b_leader = elect_one();
+    const int sig_lane = (__ballot_sync(0xffffffffu, b_leader) & 0x80000000u) ? 30 : 31;     // a lane that is not the leader
+    if (!b_leader && lane == sig_lane && p.done) {
+      // ------------------------------------------------------------------- signaller (see "Producer side")
+      uint32_t k = 0;
+      for (int it = gid; it < p.n_items; it += G, ++k) {
+        const uint32_t want = static_cast<uint32_t>(n_epi_warps) * ((k / kStoredSlots) + 1u);
+        const uint32_t addr = smem_u32(s_stored + (k % kStoredSlots));
+        uint32_t v;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        } while (v < want);
+        __threadfence();
+        atomicAdd(p.done + it / p.n_tiles, static_cast<unsigned int>(n_epi_warps));
+      }
+    }
+    if (b_leader) {
       uint32_t bs = 0, bph = 0;
       bool first = true;
       for (int it = gid; it < p.n_items; it += G) {
@@ -880,10 +912,13 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     uint32_t eseq = 0;      // items of this CTA whose residual has been requested
     auto wait_dep_seq = [&](uint32_t want) {
       if (flag_mode) {
-        while (*s_dep_seq < want) { }
-        __threadfence();
+        uint32_t v;
+        do {
+          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))) : "memory");
+        } while (v < want);
       }
     };
+    uint32_t item_k = 0;                      // index of the item among this CTA's items (slot of the shared arrival count)
     if (has_res && gid < p.n_items && n_pairs > 0) { wait_dep_seq(++eseq); prefetch_pair(gid, 0); }
     for (int it = gid; it < p.n_items; it += G) {
       const int sp = it / p.n_tiles;
@@ -941,12 +976,11 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           else if (it + G < p.n_items) { wait_dep_seq(++eseq); prefetch_pair(it + G, 0); }
         }
       }
-      if (p.done) {          // this warp's part of the item is stored: count it for the consumers (see "dependency flags")
+      if (p.done) {          // this warp's part of the item is stored: tell the signaller (see "Producer side")
         __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(p.done + sp, 1u);
-        }
+        if (lane == 0)
+          asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(s_stored + (item_k % kStoredSlots))) : "memory");
+        ++item_k;
       }
       if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back
         tc_fence_before();

@@ -296,7 +296,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const int ncta = p.two ? 2 : 1;
   p.w_rows = w->n_tile / ncta;
   p.step_bytes = static_cast<uint32_t>(p.w_rows) * rowb;
-  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 1024 /*barriers, step table*/ -
+  const size_t budget = ctx->smem_optin - 1024 /*alignment slack*/ - 1024 /*barriers, step table, flag words*/ -
                         16 * static_cast<size_t>(w->OC) /*alpha, beta (x2 when fused)*/ - 16 * kEpiStageBytes;
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
@@ -429,7 +429,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   L->block = dim3(128 + 8 * 32, 1, 1);
   L->smem = 1024 + static_cast<size_t>(p.a_stages) * p.sub_bytes + static_cast<size_t>(p.b_stages) * b_stage_bytes +
             4 * sizeof(float) * w->OC + 16 * kEpiStageBytes + 2 * (kMaxSteps + 8) +
-            8 * (2 * p.a_stages + 2 * p.b_stages + 3 * p.acc_stages) + 16;
+            8 * (2 * p.a_stages + 2 * p.b_stages + 3 * p.acc_stages) + 32;
   return DLQ_OK;
 }
 

@@ -487,7 +487,9 @@ struct dlq_resnet18 {
   cudaStream_t d2h_stream = nullptr;
   // dependency flags between the conv launches of a forward (conv_kernel.cuh "dependency flags"): per-unit completion
   // counters of every conv, one buffer sized for max_batch; [n_flags] is the timeout counter
-  bool tile_flags = true;
+  bool tile_flags = false;    // (measured, batch 256: 0.752 ms/step with flags between separate launches vs 0.740 with grid-level
+                              // dependencies - the per-SM hand-over from one launch's CTA to the next one's is what costs, and
+                              // flags do not remove it; they are what lets ONE kernel run several layers, see the conv chain)
   unsigned int* d_flags = nullptr;
   int n_flags = 0;
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one

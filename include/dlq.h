@@ -247,7 +247,7 @@ int dlq_resnet18_launches(const dlq_resnet18* m);
 /* kernels a forward of batch N really launches: 23, or 20 when the three 1x1 shortcut convs ride on conv1's launch
  * (N <= 16) */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
-/* Option "tile_flags" (default 1): consecutive conv launches of a forward depend on each other tile by tile, through
+/* Option "tile_flags" (default 0): consecutive conv launches of a forward depend on each other tile by tile, through
  * completion counters in device memory, instead of grid by grid (griddepcontrol.wait): CTAs of launch L+1 start on the
  * items whose inputs are ready while launch L drains.  0 restores grid-level dependencies (A/B measurements); results
  * are bit-identical either way.  Synchronises. */

@@ -229,12 +229,13 @@ def test_launch_count_and_span_stamps(ctx, model256):
 
 @pytest.mark.parametrize("n", [1, 9, 24, 256])
 def test_tile_dependency_flags_equal_grid_dependencies(ctx, n):
-    """tile-level dependency flags between the conv launches (the default) vs grid-level griddepcontrol.wait: identical
+    """tile-level dependency flags between the conv launches vs grid-level griddepcontrol.wait (the default): identical
     checkpoints and logits; repeated forwards and CUDA-graph replays never change a bit (a race between a consumer
     tile and its producer would); no dependency wait ever times out"""
     import torch
     import dlq_b200
     m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    m.set_option("tile_flags", 1)
     x = _tile(synth.make_input(13, min(n, 32)), n)
     want = _forward(ctx, m, x)
     if n <= 32:
