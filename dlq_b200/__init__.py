@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     "dlq_fc_weights_pack", "dlq_fc_weights_pack_i8", "dlq_fc_weights_pack_e4m3", "dlq_fc_workspace_bytes",
     "dlq_fc_forward_i8_tc", "dlq_fc_forward_fp8",
     "dlq_resnet18_submit_host", "dlq_resnet18_submit_host_u8", "dlq_resnet18_wait", "dlq_resnet18_launches_for_batch",
-    "dlq_resnet18_enable_stamps", "dlq_resnet18_read_stamps", "dlq_resnet18_set_option", "dlq_resnet18_dep_timeouts",
+    "dlq_resnet18_enable_stamps", "dlq_resnet18_read_stamps", "dlq_resnet18_set_option", "dlq_resnet18_dep_timeouts", "dlq_resnet18_plan_info",
     "dlq_multi_n_devices", "dlq_multi_set_preprocess", "dlq_multi_forward_host_u8", "dlq_multi_submit_host",
     "dlq_multi_submit_host_u8", "dlq_multi_wait", "dlq_multi_forward_device",
     "dlq_mlp_create", "dlq_mlp_destroy", "dlq_mlp_forward", "dlq_mlp_checkpoint", "dlq_mlp_weight_scales",
@@ -183,6 +183,7 @@ def load_library() -> C.CDLL:
         "dlq_resnet18_read_stamps": (i, [vp, vp, C.POINTER(i)]),
         "dlq_resnet18_set_option": (i, [vp, C.c_char_p, i]),
         "dlq_resnet18_dep_timeouts": (i, [vp, C.POINTER(C.c_uint)]),
+        "dlq_resnet18_plan_info": (i, [vp, i, C.c_char_p, C.POINTER(i)]),
         "dlq_multi_n_devices": (i, [vp]),
         "dlq_multi_set_preprocess": (i, [vp, vp, vp]),
         "dlq_multi_forward_host_u8": (i, [vp, vp, i, vp]),
@@ -592,6 +593,11 @@ class ResNet18:
 
     def set_option(self, key: str, value: int):
         self.ctx._ck(self.ctx.lib.dlq_resnet18_set_option(self.h, key.encode(), int(value)))
+
+    def plan_info(self, n: int, key: str) -> int:
+        v = C.c_int()
+        self.ctx._ck(self.ctx.lib.dlq_resnet18_plan_info(self.h, n, key.encode(), C.byref(v)))
+        return int(v.value)
 
     @property
     def dep_timeouts(self) -> int:

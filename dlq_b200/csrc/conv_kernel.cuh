@@ -212,8 +212,12 @@ __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_
   }
 }
 
+// positions of one role in the three rings (patch stages, weight stages, accumulator stages); kept by the caller so
+// that a kernel running several layers (conv_chain.cuh) carries them from one layer to the next
+struct RingState { uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0; };
+
 template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL, bool FP8, bool FUSED = false>
-__device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out) {
+__device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out, RingState& rs) {
   constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
   constexpr uint32_t SBO = 8u * ROWB;
   const uint32_t idesc = FP8 ? umma_idesc_e4m3(TWO ? 2 * kTileM : kTileM, c.n_tile) : umma_idesc_s8(TWO ? 2 * kTileM : kTileM, c.n_tile);
@@ -221,7 +225,7 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
   const uint32_t b_hi = a_hi;
   const uint32_t a_flags = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT)) + (c.sA_u32 >> 4) + c.tile_off16;
   const uint32_t b_flags = static_cast<uint32_t>(umma_smem_desc(0, 0, SBO, LAYOUT)) + (c.sB_u32 >> 4);
-  uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0;
+  uint32_t as = rs.as, aph = rs.aph, bs = rs.bs, bph = rs.bph, cs = rs.cs, cph = rs.cph;
   long long t_acc = 0, t_a = 0, t_b = 0;
   bool first_pass = true;
   for (int it = c.it_begin; it < c.it_end; it += c.it_stride) {
@@ -313,6 +317,7 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out)
     if (++cs == static_cast<uint32_t>(c.acc_stages)) { cs = 0; cph ^= 1u; }
   }
   t_out[0] = t_acc; t_out[1] = t_a; t_out[2] = t_b;
+  rs.as = as; rs.aph = aph; rs.bs = bs; rs.bph = bph; rs.cs = cs; rs.cph = cph;
 }
 
 
@@ -617,6 +622,153 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
   __syncwarp();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Epilogue warps: the items of ONE layer (the whole kernel for conv_i8_kernel; conv_chain.cuh calls it once per layer,
+// with `er` carrying the accumulator-ring position and the CTA's item count across layers).
+// The two warp groups take alternate units; the four warps of a group own the four TMEM lane quarters.
+// Flag mode (p.n_deps != 0): the residual rows of an item are requested only once the patch producer has verified that
+// item's dependencies (it publishes the number of verified items of the CTA in s_dep_seq); stores need no wait - every
+// tensor of a forward has its own buffer, and the previous forward's readers finished before this forward began.
+// ------------------------------------------------------------------------------------------------
+struct EpiShared {
+  float *s_alpha, *s_beta, *s_alpha2, *s_beta2;
+  uint8_t* s_stage;
+  uint64_t *acc_full, *acc_empty;
+  uint32_t *s_dep_seq, *s_stored;
+  uint32_t tmem_base, acc_cols;
+  int acc_stages;
+};
+struct EpiRing { uint32_t cs = 0, cph = 0, items = 0; };
+
+template <bool TWO, bool FP8>
+__device__ __forceinline__ void run_epilogue_items(const ConvKernelParams& p, const EpiShared& sh, EpiRing& er, int warp, int lane,
+                                                   int n_epi_warps, int first_it, int G, int rank, long long& t_wait) {
+  const int ew = warp - 4;
+  const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
+  const int n_groups = n_epi_warps >> 2;
+  const int grp = ew >> 2;
+  const int row = quarter * 32 + lane;                // accumulator row within the tile
+  const bool has_res = p.residual != nullptr;
+  const int cblocks = p.n_tile >> 6;
+  const int units1 = p.MT * cblocks;                   // units of the (first) conv; the fused second conv adds as many
+  const int n_units = units1 * (p.fused ? 2 : 1);
+  const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per item: grp, grp + n_groups, ...
+  const int upp = (p.acc_out || p.fused) ? 1 : 2;     // units per pass (raw-accumulator output / fused second conv: one at a time)
+  const int n_pairs = (upw + upp - 1) / upp;
+  const uint32_t tmem_base = sh.tmem_base, acc_cols = sh.acc_cols;
+  EpiCtx e;
+  e.s_alpha = sh.s_alpha; e.s_beta = sh.s_beta;
+  e.slots = sh.s_stage + ew * 2 * kEpiStageBytes;
+  e.lane = lane; e.crow = lane >> 2; e.cq = lane & 3;
+  e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = 0;
+  e.out = p.out; e.out_PR = p.out_PR;
+  e.relu_mask = p.relu ? 0xFFFFFFFFu : 0u;
+  e.res_mul = p.res_mul;
+  // global position of this lane's row in tile mt of super-tile st (rows past the super-tile's own positions
+  // belong to the next super-tile: mapped to total_pos, which decodes as image N = invalid)
+  auto own_pos = [&](int st, int mt) {
+    const int local = mt * kTileM + row;
+    return local < p.super_stride ? st * p.super_stride + local : p.total_pos;
+  };
+  auto prefetch_pair = [&](int it, int pi) {
+    const int sp = it / p.n_tiles;
+    const int nt = it - sp * p.n_tiles;
+    const int st = TWO ? 2 * sp + rank : sp;
+    e.n0 = nt * p.n_tile;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = upp * pi + u;
+      if (u < upp && k < upw) {
+        const int unit = grp + k * n_groups;
+        const int mt = unit / cblocks, cb = unit - mt * cblocks;
+        epi_prefetch_res(p, e, u, own_pos(st, mt), cb << 6);
+      }
+    }
+    cp_async_commit();
+  };
+  uint32_t cs = er.cs, cph = er.cph;
+  const bool flag_mode = p.n_deps != 0;
+  auto wait_dep_seq = [&](uint32_t want) {             // until the patch producer has verified `want` items of this CTA
+    if (flag_mode) {
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sh.s_dep_seq)) : "memory");
+      } while (v < want);
+    }
+  };
+  if (has_res && first_it < p.n_items && n_pairs > 0) { wait_dep_seq(er.items + 1u); prefetch_pair(first_it, 0); }
+  for (int it = first_it; it < p.n_items; it += G) {
+    const int sp = it / p.n_tiles;
+    const int nt = it - sp * p.n_tiles;
+    const int st = TWO ? 2 * sp + rank : sp;
+    const uint32_t acc_empty_addr = TWO ? leader_cta_addr(&sh.acc_empty[cs]) : smem_u32(&sh.acc_empty[cs]);
+    const long long tw = dbg_clock();
+    mbar_wait(&sh.acc_full[cs], cph);
+    t_wait += dbg_clock() - tw;
+    tc_fence_after();
+    const int np = (dbg_flags(p.dbg) & 1) ? 0 : n_pairs;
+    for (int pi = 0; pi < np; ++pi) {
+      uint32_t taddr[2];
+      int c0[2], g_own[2];
+      const int nu = (upp == 2 && 2 * pi + 1 < upw) ? 2 : 1;
+      e.n0 = nt * p.n_tile;
+      // (fused launches process one unit per pass, so a pass never mixes the two convs)
+      const int unit0 = grp + upp * pi * n_groups;
+      const bool second = unit0 >= units1;
+      e.s_alpha = (second ? sh.s_alpha2 : sh.s_alpha) + e.n0;
+      e.s_beta = (second ? sh.s_beta2 : sh.s_beta) + e.n0;
+      e.out = second ? p.out2 : p.out;
+      e.out_PR = second ? p.out2_PR : p.out_PR;
+      e.out_pitch = p.Ho + e.out_PR;
+      e.relu_mask = (second ? p.relu2 : p.relu) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
+        if (second) unit -= units1;
+        const int mt = unit / cblocks, cb = unit - mt * cblocks;
+        c0[u] = cb << 6;
+        g_own[u] = own_pos(st, mt);
+        taddr[u] = tmem_base + cs * acc_cols + (second ? static_cast<uint32_t>(p.MT) * p.n_tile : 0u) +
+                   static_cast<uint32_t>(mt) * p.n_tile + c0[u] + (static_cast<uint32_t>(quarter * 32) << 16);
+      }
+      const bool last = pi == np - 1;
+      if (has_res) {
+        cp_async_wait_all();
+        __syncwarp();
+      }
+#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC, FP8>(p, e, taddr, c0, g_own, last, acc_empty_addr)
+#define DLQ_EPI_SHAPES(RES)                                       \
+  do {                                                            \
+    if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \
+    else if (c0[0] == c0[1]) DLQ_EPI(RES, 2, true, false);        \
+    else DLQ_EPI(RES, 2, false, false);                           \
+  } while (0)
+      if (p.acc_out) { if (has_res) DLQ_EPI(true, 1, true, true); else DLQ_EPI(false, 1, true, true); }
+      else if (has_res) DLQ_EPI_SHAPES(true);
+      else DLQ_EPI_SHAPES(false);
+#undef DLQ_EPI_SHAPES
+#undef DLQ_EPI
+      if (has_res) {
+        if (pi + 1 < n_pairs) prefetch_pair(it, pi + 1);
+        else if (it + G < p.n_items) { wait_dep_seq(er.items + 2u); prefetch_pair(it + G, 0); }
+      }
+    }
+    // this warp's part of the item is stored: tell the signaller (see "Producer side"; it publishes only if p.done)
+    __syncwarp();
+    if (lane == 0)
+      asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(sh.s_stored + (er.items % kStoredSlots))) : "memory");
+    ++er.items;
+    if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
+    }
+    if (++cs == static_cast<uint32_t>(sh.acc_stages)) { cs = 0; cph ^= 1u; }
+  }
+  if (has_res) cp_async_wait_all();
+  er.cs = cs; er.cph = cph;
+}
+
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring: a_stages * sub_bytes][B ring: b_stages * step_bytes(1024-aligned)][alpha, beta: 2*OC f32]
 //   [epilogue staging: 8 warps * 2 slots * kEpiStageBytes][step offsets][barriers][tmem slot]
@@ -729,12 +881,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         wait_deps(p, g0, min(g0 + p.super_stride, p.total_pos) - 1, lane);
       }
       if (leader) {
-        if (p.n_deps) {
-          // (the polling lanes' acquires reach this lane through wait_deps' __syncwarp: causality order is transitive)
-          fence_proxy_async_all();   // producer's generic-proxy stores before this thread's async-proxy (TMA) reads
-          ++seq;                     // the epilogue warps may now prefetch this item's residual rows
-          asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))), "r"(seq) : "memory");
-        }
+        // (the polling lanes' acquires reach this lane through wait_deps' __syncwarp: causality order is transitive)
+        if (p.n_deps) fence_proxy_async_all();   // producer's generic-proxy stores before this thread's async-proxy (TMA) reads
+        ++seq;                                   // the epilogue warps may now prefetch this item's residual rows
+        asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))), "r"(seq) : "memory");
         const int v0 = (st * p.super_stride) / p.Wp;
         for (int s = 0; s < p.n_sub; ++s) {
           const long long tw = dbg_clock();
@@ -827,20 +977,21 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     c.leader = elect_one();
     c.dbg = p.dbg;
     long long tt[3] = {0, 0, 0};
+    RingState rs;
     const long long t_begin = dbg_clock();
     if (k_split) {
       constexpr int KA = K32 >= 2 ? 1 : 0, KB = K32 >= 2 ? 2 : 0;   // (K32 == 1 never takes this branch)
       if (p.fused) {      // (the fused shortcut conv forces one tile per item, hence this branch)
-        if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8, true>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8, true>(c, tt); }
-        else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8, true>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8, true>(c, tt); }
-      } else if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt); }
-      else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, KB, FP8>(c, tt); }
+        if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8, true>(c, tt, rs); else run_issuer<ROWB, 1, true, TWO, KB, FP8, true>(c, tt, rs); }
+        else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8, true>(c, tt, rs); else run_issuer<ROWB, 1, false, TWO, KB, FP8, true>(c, tt, rs); }
+      } else if (p.b_resident) { if (issuer == 0) run_issuer<ROWB, 1, true, TWO, KA, FP8>(c, tt, rs); else run_issuer<ROWB, 1, true, TWO, KB, FP8>(c, tt, rs); }
+      else { if (issuer == 0) run_issuer<ROWB, 1, false, TWO, KA, FP8>(c, tt, rs); else run_issuer<ROWB, 1, false, TWO, KB, FP8>(c, tt, rs); }
     } else if (p.fused) {     // (one tile per item and no K split: the E4M3 network's fused shortcut, or the 32-byte stem rows)
-      if (p.b_resident) run_issuer<ROWB, 1, true, TWO, 0, FP8, true>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0, FP8, true>(c, tt);
+      if (p.b_resident) run_issuer<ROWB, 1, true, TWO, 0, FP8, true>(c, tt, rs); else run_issuer<ROWB, 1, false, TWO, 0, FP8, true>(c, tt, rs);
     } else if (p.b_resident) {
-      if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, true, TWO, 0, FP8>(c, tt);
+      if (my_mt == 2) run_issuer<ROWB, 2, true, TWO, 0, FP8>(c, tt, rs); else run_issuer<ROWB, 1, true, TWO, 0, FP8>(c, tt, rs);
     } else {
-      if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0, FP8>(c, tt); else run_issuer<ROWB, 1, false, TWO, 0, FP8>(c, tt);
+      if (my_mt == 2) run_issuer<ROWB, 2, false, TWO, 0, FP8>(c, tt, rs); else run_issuer<ROWB, 1, false, TWO, 0, FP8>(c, tt, rs);
     }
     if (p.dbg_times && c.leader && issuer == 0) {
       long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
@@ -849,52 +1000,8 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
-    // The two warp groups take alternate units; the four warps of a group own the four TMEM lane quarters.
-    const int ew = warp - 4;
-    const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
-    const int n_groups = n_epi_warps >> 2;
-    const int grp = ew >> 2;
-    const int row = quarter * 32 + lane;                // accumulator row within the tile
-    const bool has_res = p.residual != nullptr;
-    const int cblocks = p.n_tile >> 6;
-    const int units1 = p.MT * cblocks;                   // units of the (first) conv; the fused second conv adds as many
-    const int n_units = units1 * (p.fused ? 2 : 1);
-    const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per item: grp, grp + n_groups, ...
-    const int upp = (p.acc_out || p.fused) ? 1 : 2;     // units per pass (raw-accumulator output / fused second conv: one at a time)
-    const int n_pairs = (upw + upp - 1) / upp;
-    EpiCtx e;
-    e.s_alpha = s_alpha; e.s_beta = s_beta;
-    e.slots = s_stage + ew * 2 * kEpiStageBytes;
-    e.lane = lane; e.crow = lane >> 2; e.cq = lane & 3;
-    e.out_pitch = p.Ho + p.out_PR; e.res_pitch = p.Ho + p.res_PR; e.n0 = 0;
-    e.out = p.out; e.out_PR = p.out_PR;
-    e.relu_mask = p.relu ? 0xFFFFFFFFu : 0u;
-    e.res_mul = p.res_mul;
-    // global position of this lane's row in tile mt of super-tile st (rows past the super-tile's own positions
-    // belong to the next super-tile: mapped to total_pos, which decodes as image N = invalid)
-    auto own_pos = [&](int st, int mt) {
-      const int local = mt * kTileM + row;
-      return local < p.super_stride ? st * p.super_stride + local : p.total_pos;
-    };
-    auto prefetch_pair = [&](int it, int pi) {
-      const int sp = it / p.n_tiles;
-      const int nt = it - sp * p.n_tiles;
-      const int st = TWO ? 2 * sp + rank : sp;
-      e.n0 = nt * p.n_tile;
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int k = upp * pi + u;
-        if (u < upp && k < upw) {
-          const int unit = grp + k * n_groups;
-          const int mt = unit / cblocks, cb = unit - mt * cblocks;
-          epi_prefetch_res(p, e, u, own_pos(st, mt), cb << 6);
-        }
-      }
-      cp_async_commit();
-    };
-    uint32_t cs = 0, cph = 0;
-    long long t_wait = 0;
     const long long t_begin = dbg_clock();
+    long long t_wait = 0;
     // per-channel constants -> shared memory (kernel-lifetime constants, not produced by the previous kernel), while
     // the first patch / weight loads and MMAs are in flight; the epilogue warps meet on named barrier 1
     for (int i = static_cast<int>(threadIdx.x) - 128; i < p.OC; i += n_epi_warps * 32) {
@@ -903,94 +1010,16 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
       if (p.fused) { s_alpha2[i] = p.alpha2[i]; s_beta2[i] = p.beta2[i]; }
     }
     asm volatile("bar.sync 1, %0;" ::"r"(n_epi_warps * 32) : "memory");
-    // grid-level mode: the residual is an earlier kernel's output, and our stores must not race its readers.  Flag mode:
-    // the residual rows of item k are read only once the patch producer has verified item k's dependencies (it
-    // publishes the count of verified items in s_dep_seq); stores need no wait - every tensor of a forward has its own
-    // buffer, and the previous forward's readers finished before this forward began.
-    const bool flag_mode = p.n_deps != 0;
-    if (!flag_mode) pdl_wait();
-    uint32_t eseq = 0;      // items of this CTA whose residual has been requested
-    auto wait_dep_seq = [&](uint32_t want) {
-      if (flag_mode) {
-        uint32_t v;
-        do {
-          asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))) : "memory");
-        } while (v < want);
-      }
-    };
-    uint32_t item_k = 0;                      // index of the item among this CTA's items (slot of the shared arrival count)
-    if (has_res && gid < p.n_items && n_pairs > 0) { wait_dep_seq(++eseq); prefetch_pair(gid, 0); }
-    for (int it = gid; it < p.n_items; it += G) {
-      const int sp = it / p.n_tiles;
-      const int nt = it - sp * p.n_tiles;
-      const int st = TWO ? 2 * sp + rank : sp;
-      const uint32_t acc_empty_addr = TWO ? leader_cta_addr(&acc_empty[cs]) : smem_u32(&acc_empty[cs]);
-      const long long tw = dbg_clock();
-      mbar_wait(&acc_full[cs], cph);
-      t_wait += dbg_clock() - tw;
-      tc_fence_after();
-      const int np = (dbg_flags(p.dbg) & 1) ? 0 : n_pairs;
-      for (int pi = 0; pi < np; ++pi) {
-        uint32_t taddr[2];
-        int c0[2], g_own[2];
-        const int nu = (upp == 2 && 2 * pi + 1 < upw) ? 2 : 1;
-        e.n0 = nt * p.n_tile;
-        // (fused launches process one unit per pass, so a pass never mixes the two convs)
-        const int unit0 = grp + upp * pi * n_groups;
-        const bool second = unit0 >= units1;
-        e.s_alpha = (second ? s_alpha2 : s_alpha) + e.n0;
-        e.s_beta = (second ? s_beta2 : s_beta) + e.n0;
-        e.out = second ? p.out2 : p.out;
-        e.out_PR = second ? p.out2_PR : p.out_PR;
-        e.out_pitch = p.Ho + e.out_PR;
-        e.relu_mask = (second ? p.relu2 : p.relu) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
-          if (second) unit -= units1;
-          const int mt = unit / cblocks, cb = unit - mt * cblocks;
-          c0[u] = cb << 6;
-          g_own[u] = own_pos(st, mt);
-          taddr[u] = tmem_base + cs * acc_cols + (second ? static_cast<uint32_t>(p.MT) * p.n_tile : 0u) +
-                     static_cast<uint32_t>(mt) * p.n_tile + c0[u] + (static_cast<uint32_t>(quarter * 32) << 16);
-        }
-        const bool last = pi == np - 1;
-        if (has_res) {
-          cp_async_wait_all();
-          __syncwarp();
-        }
-#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC, FP8>(p, e, taddr, c0, g_own, last, acc_empty_addr)
-#define DLQ_EPI_SHAPES(RES)                                       \
-  do {                                                            \
-    if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \
-    else if (c0[0] == c0[1]) DLQ_EPI(RES, 2, true, false);        \
-    else DLQ_EPI(RES, 2, false, false);                           \
-  } while (0)
-        if (p.acc_out) { if (has_res) DLQ_EPI(true, 1, true, true); else DLQ_EPI(false, 1, true, true); }
-        else if (has_res) DLQ_EPI_SHAPES(true);
-        else DLQ_EPI_SHAPES(false);
-#undef DLQ_EPI_SHAPES
-#undef DLQ_EPI
-        if (has_res) {
-          if (pi + 1 < n_pairs) prefetch_pair(it, pi + 1);
-          else if (it + G < p.n_items) { wait_dep_seq(++eseq); prefetch_pair(it + G, 0); }
-        }
-      }
-      if (p.done) {          // this warp's part of the item is stored: tell the signaller (see "Producer side")
-        __syncwarp();
-        if (lane == 0)
-          asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(s_stored + (item_k % kStoredSlots))) : "memory");
-        ++item_k;
-      }
-      if (np == 0) {                                    // (debug: epilogue skipped) still hand the stage back
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
-      }
-      if (++cs == static_cast<uint32_t>(p.acc_stages)) { cs = 0; cph ^= 1u; }
-    }
-    if (has_res) cp_async_wait_all();
-    if (p.dbg_times && ew == 0 && lane == 0) {
+    // grid-level mode: the residual is an earlier kernel's output, and our stores must not race its readers (flag mode:
+    // see run_epilogue_items)
+    if (p.n_deps == 0) pdl_wait();
+    EpiShared sh;
+    sh.s_alpha = s_alpha; sh.s_beta = s_beta; sh.s_alpha2 = s_alpha2; sh.s_beta2 = s_beta2; sh.s_stage = s_stage;
+    sh.acc_full = acc_full; sh.acc_empty = acc_empty; sh.s_dep_seq = const_cast<uint32_t*>(s_dep_seq); sh.s_stored = s_stored;
+    sh.tmem_base = tmem_base; sh.acc_cols = acc_cols; sh.acc_stages = p.acc_stages;
+    EpiRing er;
+    run_epilogue_items<TWO, FP8>(p, sh, er, warp, lane, n_epi_warps, gid, G, rank, t_wait);
+    if (p.dbg_times && warp == 4 && lane == 0) {
       long long* d = p.dbg_times + static_cast<size_t>(blockIdx.x) * 16;
       d[4] = dbg_clock() - t_begin; d[5] = t_wait;
     }

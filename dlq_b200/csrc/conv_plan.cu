@@ -194,7 +194,7 @@ int pack_conv_weights(dlq_ctx* ctx, const int8_t* wq, int OC, int IC, int kH, in
 
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
               const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L,
-              const SecondConv* second) {
+              const SecondConv* second, bool allow_resident) {
   ConvKernelParams& p = L->p;
   memset(&p, 0, sizeof(p));
   L->fp8 = w->fp8;
@@ -310,7 +310,7 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
     p.tma_bytes = NR * p.Wp * rowb;
     p.sub_bytes = (p.tma_bytes + 1023) & ~1023;
     // weights resident in smem when they are small (stem, layer1, stride-2 / 1x1 convs): no per-item re-fetch
-    p.b_resident = (n_tiles == 1 && all_b <= 80 * 1024 && all_b + 2 * static_cast<size_t>(p.sub_bytes) <= budget) ? 1 : 0;
+    p.b_resident = (allow_resident && n_tiles == 1 && all_b <= 80 * 1024 && all_b + 2 * static_cast<size_t>(p.sub_bytes) <= budget) ? 1 : 0;
     const int min_a = 2;
     if (p.b_resident) {
       p.b_stages = p.n_steps;
@@ -516,6 +516,8 @@ int configure_conv_kernels(dlq_ctx* ctx) {
   DLQ_CUDA(ctx, (configure_t<32, true, true>(ctx)));
   DLQ_CUDA(ctx, (configure_t<64, true, true>(ctx)));
   DLQ_CUDA(ctx, (configure_t<128, true, true>(ctx)));
+  DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
   return DLQ_OK;
 }
 
@@ -538,6 +540,95 @@ void conv_add_dep(ConvLaunch* consumer, const ConvLaunch& producer, int s, int l
   d.unit = q.super_stride * ncta;
   d.Pv = q.Pv; d.Wp = q.Wp; d.Wo = q.Wo; d.H = q.Ho;
   d.s = s; d.lo = lo; d.hi = hi;
+}
+
+// ---- conv chain (conv_chain.cuh)
+int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, ChainLaunch* out) {
+  DLQ_ARG(ctx, n_layers >= 1 && n_layers <= kMaxChainLayers, "conv chain: 1 .. kMaxChainLayers layers");
+  ChainParams& cp = out->cp;
+  memset(&cp, 0, sizeof(cp));
+  out->fp8 = layers[0]->fp8;
+  int a_stage = 0, b_stage = 0, oc_max = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    const ConvLaunch& L = *layers[l];
+    const ConvKernelParams& p = L.p;
+    DLQ_ARG(ctx, L.rowb == 128 && p.two == 1 && p.MT == 2 && p.n_tile == 128 && p.acc_stages == 2 && !p.fused && !p.b_resident &&
+                     !p.acc_out && L.fp8 == out->fp8 && p.alpha && p.beta && p.n_steps <= kMaxSteps,
+            "conv chain: a layer does not have the chain's static configuration");
+    a_stage = std::max(a_stage, p.sub_bytes);
+    b_stage = std::max(b_stage, static_cast<int>((p.step_bytes + 1023u) & ~1023u));
+    oc_max = std::max(oc_max, p.OC);
+  }
+  const size_t fixed = 1024 /*alignment slack*/ + 2 * sizeof(float) * oc_max + 16 * kEpiStageBytes + 2 * 2 * (kMaxSteps + 8) + 1024;
+  DLQ_ARG(ctx, ctx->smem_optin > fixed + 2 * static_cast<size_t>(a_stage) + 3 * static_cast<size_t>(b_stage), "conv chain: does not fit shared memory");
+  const size_t budget = ctx->smem_optin - fixed;
+  int b_stages = static_cast<int>(std::min<size_t>(8, (budget - 2 * static_cast<size_t>(a_stage)) / b_stage));
+  int a_stages = static_cast<int>(std::min<size_t>(4, (budget - static_cast<size_t>(b_stages) * b_stage) / a_stage));
+  DLQ_ARG(ctx, a_stages >= 2 && b_stages >= 3, "conv chain: rings too shallow");
+  cp.n_layers = n_layers;
+  cp.a_stages = a_stages; cp.b_stages = b_stages;
+  cp.a_stage_bytes = a_stage; cp.b_stage_bytes = b_stage;
+  cp.oc_max = oc_max;
+  // one CTA pair per SM pair, all co-resident (the CTAs wait for each other through the dependency flags)
+  int G = ctx->num_sms / 2;
+  out->block = dim3(128 + 8 * 32, 1, 1);
+  out->smem = 1024 + static_cast<size_t>(a_stages) * a_stage + static_cast<size_t>(b_stages) * b_stage + 2 * sizeof(float) * oc_max +
+              16 * kEpiStageBytes + 2 * 2 * (kMaxSteps + 8) + 8 * (2 * a_stages + 2 * b_stages + 4) + 32;
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * G), 1, 1);
+    cfg.blockDim = out->block;
+    cfg.dynamicSmemBytes = out->smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    const cudaError_t e = out->fp8 ? cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel<true>, &cfg)
+                                   : cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel<false>, &cfg);
+    if (e == cudaSuccess && max_clusters > 0) G = std::min(G, max_clusters);
+    else cudaGetLastError();
+  }
+  out->grid = dim3(static_cast<unsigned>(2 * G), 1, 1);
+  long long shift = 0;
+  for (int l = 0; l < n_layers; ++l) {
+    ChainLayer& C = cp.layer[l];
+    C.p = layers[l]->p;
+    C.tm0 = layers[l]->tmap;
+    C.tmw = layers[l]->tmap_w;
+    C.item_shift = static_cast<int>(shift % G);       // the chain's items are dealt round-robin across layer boundaries
+    shift += C.p.n_items;
+  }
+  return DLQ_OK;
+}
+
+int launch_chain(dlq_ctx* ctx, ChainLaunch& C) {
+  for (;;) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = C.grid;
+    cfg.blockDim = C.block;
+    cfg.dynamicSmemBytes = C.smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[3];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;       // every CTA pair resident at once
+    attr[1].val.cooperative = 1;
+    attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[2].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (C.pdl && !ctx->no_pdl) ? 3 : 2;
+    const cudaError_t e = C.fp8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, C.cp)
+                                : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, C.cp);
+    if (e == cudaSuccess) return DLQ_OK;
+    if (cfg.numAttrs == 3) {       // cooperative + programmatic serialization refused together: keep the cooperative one
+      cudaGetLastError();
+      C.pdl = false;
+      continue;
+    }
+    DLQ_CUDA(ctx, e);
+  }
 }
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {

@@ -493,6 +493,9 @@ struct dlq_resnet18 {
   unsigned int* d_flags = nullptr;
   int n_flags = 0;
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
+  bool conv_chain = true;     // batches above kFuseMaxBatch: the blocks from chain_first_block on as one persistent launch
+  int chain_start = 8;        // conv index of the chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block; everything
+                              // behind it belongs to the chain.  8 = layer2.0.conv2: the thirteen convs with 128-byte K rows
   // span stamps: ring of [forward][launch][2] globaltimer values (dlq_resnet18_enable_stamps)
   unsigned long long* d_stamps = nullptr;
   int stamp_ring = 0;
@@ -502,6 +505,11 @@ struct dlq_resnet18 {
     ConvLaunch L[DLQ_NUM_CONVS];
     bool fused[8] = {false};    // block b's shortcut conv runs inside L[conv1 of b]
     int flag_units = 0;         // dependency counters this plan uses
+    // blocks chain_from .. 7 run as ONE persistent cooperative launch (conv_chain.cuh); chain_slot[l] = conv index of layer l
+    bool has_chain = false;
+    int chain_first_conv = 0;   // the chain member the forward's launch order reaches first (conv1 of the first chained block)
+    ChainLaunch chain;
+    int chain_conv[kMaxChainLayers] = {0};
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
@@ -552,6 +560,17 @@ inline int act_out(int b) { return 4 + 3 * b; }
 constexpr int kActInput = 0, kActStem = 1, kActGap = 26;
 constexpr int kFuseMaxBatch = 16;
 
+int build_plan_without_chain(dlq_resnet18* m, int N, dlq_resnet18::Plan* P);
+
+// conv index i belongs to the chain that starts at conv `start` (conv1 = 1 + 3b or conv2 = 2 + 3b of a block b): the convs of
+// the later blocks, conv2 of the start block, and - when the chain starts with conv1 - the start block's conv1 and shortcut
+bool chain_member(int start, int i) {
+  if (start >= DLQ_NUM_CONVS || i < 1) return false;
+  const int sb = (start - 1) / 3, b = (i - 1) / 3;
+  if (b != sb) return b > sb;
+  return (start - 1) % 3 == 0 || i == start;
+}
+
 int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   dlq_ctx* ctx = m->ctx;
   P->N = N;
@@ -561,6 +580,9 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   if (rc != DLQ_OK) return rc;
   Act cur = with_n(m->a_pool, N);
   float s_cur = S[kActStem];
+  // the layers of the conv chain stream their weights (one static ring layout for every layer, conv_chain.cuh)
+  const int chain_start = (m->conv_chain && N > kFuseMaxBatch) ? m->chain_start : DLQ_NUM_CONVS;
+  auto in_chain = [&](int i) { return chain_member(chain_start, i); };
   for (int b = 0; b < 8; ++b) {
     const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, id = 3 + 3 * b;
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
@@ -573,20 +595,20 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
       sc.alpha = m->d_alpha[id]; sc.beta = m->d_beta[id]; sc.relu = 0; sc.out = with_n(m->a_ds[b], N);
       rc = plan_conv(ctx, m->conv_fused[b], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1], &sc);
     } else {
-      rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1]);
+      rc = plan_conv(ctx, m->conv[i1], cur, t1, m->d_alpha[i1], m->d_beta[i1], nullptr, 0.f, 1, nullptr, &P->L[i1], nullptr, !in_chain(i1));
     }
     if (rc != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       Act ds = with_n(m->a_ds[b], N);
       if (!P->fused[b]) {
-        rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, nullptr, &P->L[id]);
+        rc = plan_conv(ctx, m->conv[id], cur, ds, m->d_alpha[id], m->d_beta[id], nullptr, 0.f, 0, nullptr, &P->L[id], nullptr, !in_chain(id));
         if (rc != DLQ_OK) return rc;
       }
       rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &ds, dlq_res_mul(S[act_ds(b)], S[act_out(b)]), 1,
-                     nullptr, &P->L[i2]);
+                     nullptr, &P->L[i2], nullptr, !in_chain(i2));
     } else {
       rc = plan_conv(ctx, m->conv[i2], t1, o, m->d_alpha[i2], m->d_beta[i2], &cur, dlq_res_mul(s_cur, S[act_out(b)]), 1,
-                     nullptr, &P->L[i2]);
+                     nullptr, &P->L[i2], nullptr, !in_chain(i2));
     }
     if (rc != DLQ_OK) return rc;
     cur = o;
@@ -596,18 +618,23 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   // for the units of its producers instead of for their whole grids.  (The stem, the max-pool behind it and the first
   // block's conv1 keep the grid-level dependency: their producers are not conv launches.)
   int units = 0;
-  auto keep = [&](ConvLaunch& L) {
+  auto keep = [&](int i) {
+    ConvLaunch& L = P->L[i];
     const int n = conv_flag_units(L);
-    if (m->d_flags && m->tile_flags && units + n <= m->n_flags) conv_set_flags(&L, m->d_flags + units, m->d_flags + m->n_flags);
+    if (m->d_flags && (m->tile_flags || in_chain(i)) && units + n <= m->n_flags)
+      conv_set_flags(&L, m->d_flags + units, m->d_flags + m->n_flags);
     units += n;
   };
   for (int b = 0; b < 8; ++b) {
-    keep(P->L[1 + 3 * b]);
-    if (kBlocks[b].down && !P->fused[b]) keep(P->L[3 + 3 * b]);
-    keep(P->L[2 + 3 * b]);
+    keep(1 + 3 * b);
+    if (kBlocks[b].down && !P->fused[b]) keep(3 + 3 * b);
+    keep(2 + 3 * b);
   }
   P->flag_units = units;
-  if (m->d_flags && m->tile_flags && units <= m->n_flags) {
+  P->has_chain = false;
+  // (conv_add_dep ignores producers that keep no counters: without "tile_flags" only the convs of the chain depend on each
+  // other through flags, and whatever they read from before the chain is covered by the chain's one grid-level wait)
+  if (m->d_flags && units <= m->n_flags) {
     const ConvLaunch* prev_out = nullptr;      // the conv that produced this block's input (null: the max-pool)
     for (int b = 0; b < 8; ++b) {
       ConvLaunch& c1 = P->L[1 + 3 * b];
@@ -629,8 +656,31 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
       else if (prev_out) conv_add_dep(&c2, *prev_out, 1, 0, 0);            // identity skip = the block input
       prev_out = &c2;
     }
+    if (chain_start < DLQ_NUM_CONVS) {
+      const ConvLaunch* layers[kMaxChainLayers + 3];
+      int n = 0;
+      // (the 1x1 shortcut conv goes FIRST in its block: conv2 needs its rows as residual, and behind conv1 they would be
+      // the last thing every CTA produces before conv2's first items ask for them - measured: 25 us instead of 17 for conv2)
+      for (int b = 0; b < 8 && n <= kMaxChainLayers; ++b) {
+        const int order[3] = {3 + 3 * b, 1 + 3 * b, 2 + 3 * b};
+        for (int i : order)
+          if (in_chain(i) && (i != 3 + 3 * b || kBlocks[b].down)) { P->chain_conv[std::min(n, kMaxChainLayers - 1)] = i; layers[n++] = &P->L[i]; }
+      }
+      // (too many layers, or one without the chain's static configuration: the blocks simply stay separate launches)
+      P->chain_first_conv = chain_start;
+      if (n <= kMaxChainLayers && plan_chain(ctx, layers, n, &P->chain) == DLQ_OK) P->has_chain = true;
+      else if (!m->tile_flags) return build_plan_without_chain(m, N, P);
+    }
   }
   return DLQ_OK;
+}
+
+int build_plan_without_chain(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
+  const bool keep = m->conv_chain;
+  m->conv_chain = false;
+  const int rc = build_plan(m, N, P);
+  m->conv_chain = keep;
+  return rc;
 }
 
 }  // namespace
@@ -812,7 +862,17 @@ int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
   int fused = 0;
   for (int b = 0; b < 8; ++b)
     if (kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= kFuseMaxBatch) ++fused;
-  return 23 - fused;
+  int chained = 0;       // convs that share the one chain launch (conv_chain.cuh)
+  if (N <= m->max_batch) {
+    dlq_resnet18* mm = const_cast<dlq_resnet18*>(m);      // (the plan cache is logically mutable)
+    auto it = mm->plans.find(N);
+    if (it == mm->plans.end()) {
+      std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
+      if (cudaSetDevice(m->ctx->device) == cudaSuccess && build_plan(mm, N, P.get()) == DLQ_OK) it = mm->plans.emplace(N, std::move(P)).first;
+    }
+    if (it != mm->plans.end() && it->second->has_chain) chained = it->second->chain.cp.n_layers - 1;
+  }
+  return 23 - fused - chained;
 }
 
 // x: fp32 NCHW input, or (x == nullptr) x_u8: uint8 HWC images mapped through m->d_lut
@@ -829,11 +889,11 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
     if (rc != DLQ_OK) return rc;
     it = m->plans.emplace(N, std::move(P)).first;
   }
-  const dlq_resnet18::Plan& P = *it->second;
+  dlq_resnet18::Plan& P = *it->second;
   const float* S = m->act_scale;
   // dependency counters: zero at the start of every forward - the last kernel of the previous one cleared them; only a
   // forward that failed half-way leaves them dirty
-  const bool flags_on = m->tile_flags && m->d_flags && P.flag_units <= m->n_flags;
+  const bool flags_on = (m->tile_flags || P.has_chain) && m->d_flags && P.flag_units <= m->n_flags;
   if (m->flags_dirty && m->d_flags)
     DLQ_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, static_cast<size_t>(m->n_flags) * sizeof(unsigned int), ctx->stream));
   m->flags_dirty = flags_on;
@@ -848,8 +908,29 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   ++m->fwd_count;
   int slot = 0;
   auto stamp = [&]() -> unsigned long long* { unsigned long long* r = st_base ? st_base + 2 * slot : nullptr; ++slot; return r; };
-  auto conv = [&](const ConvLaunch& L0) -> int {
+  // conv index i of the plan: its own launch, or - for the layers of the chain - the chain's one launch at its first layer
+  auto conv = [&](int i) -> int {
     unsigned long long* sp = stamp();
+    if (P.has_chain) {
+      for (int l = 0; l < P.chain.cp.n_layers; ++l)
+        if (P.chain_conv[l] == i) {
+          if (i != P.chain_first_conv) return DLQ_OK;      // (launched once, where the forward reaches its first member)
+          if (!sp) return launch_chain(ctx, P.chain);
+          std::unique_ptr<ChainLaunch> C(new ChainLaunch(P.chain));      // (measurement only: per-layer stamp slots)
+          for (int k = 0; k < C->cp.n_layers; ++k) {
+            // slot of conv index j in launch order: 1 stem, then per block conv1, [downsample], conv2 behind the max-pool
+            const int j = P.chain_conv[k], b = (j - 1) / 3, r = (j - 1) % 3;
+            int pos = 3;
+            for (int bb = 0; bb < b; ++bb) pos += kBlocks[bb].down ? 3 : 2;
+            pos += r == 0 ? 0 : r == 2 ? 1 : (kBlocks[b].down ? 2 : 1);
+            C->cp.layer[k].p.stamps = st_base + 2 * pos;
+          }
+          const int rc = launch_chain(ctx, *C);
+          P.chain.pdl = C->pdl;
+          return rc;
+        }
+    }
+    const ConvLaunch& L0 = P.L[i];
     if (!sp) return launch_conv(ctx, L0);
     ConvLaunch L = L0;
     L.p.stamps = sp;
@@ -861,26 +942,26 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
          : preprocess_u8_s2d(ctx, x_u8, N, 224, 224, m->d_lut, with_n(m->a_in, N), stamp());
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
-  rc = conv(P.L[0]);
+  rc = conv(0);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   rc = maxpool_act(ctx, with_n(m->a_stem, N), with_n(m->a_pool, N), stamp());
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   for (int b = 0; b < 8; ++b) {
-    rc = conv(P.L[1 + 3 * b]);
+    rc = conv(1 + 3 * b);
     if (rc != DLQ_OK) return rc;
     if ((rc = mark()) != DLQ_OK) return rc;
     if (kBlocks[b].down) {
       if (!P.fused[b]) {          // (fused: the shortcut conv ran inside conv1's launch; its profile entry stays 0)
-        rc = conv(P.L[3 + 3 * b]);
+        rc = conv(3 + 3 * b);
         if (rc != DLQ_OK) return rc;
       } else {
         (void)stamp();
       }
       if ((rc = mark()) != DLQ_OK) return rc;
     }
-    rc = conv(P.L[2 + 3 * b]);
+    rc = conv(2 + 3 * b);
     if (rc != DLQ_OK) return rc;
     if ((rc = mark()) != DLQ_OK) return rc;
   }
@@ -911,10 +992,18 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   if (!m) return DLQ_ERR_ARG;
   dlq_ctx* ctx = m->ctx;
   DLQ_ARG(ctx, key != nullptr, "null key");
-  DLQ_ARG(ctx, std::string(key) == "tile_flags", "unknown option (tile_flags)");
+  const std::string k(key);
+  DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start",
+          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start)");
+  DLQ_ARG(ctx, k != "chain_first_block" || (value >= 1 && value <= 7), "chain_first_block outside 1..7");
+  DLQ_ARG(ctx, k != "chain_start" || (value >= 1 && value < DLQ_NUM_CONVS && (value - 1) % 3 != 2),
+          "chain_start must be the index of a block's conv1 (1 + 3b) or conv2 (2 + 3b)");
   DLQ_CUDA(ctx, cudaSetDevice(ctx->device));
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  m->tile_flags = value != 0;
+  if (k == "tile_flags") m->tile_flags = value != 0;
+  else if (k == "conv_chain") m->conv_chain = value != 0;
+  else if (k == "chain_first_block") m->chain_start = 1 + 3 * value;
+  else m->chain_start = value;
   m->plans.clear();
   if (m->graph_exec) { cudaGraphExecDestroy(m->graph_exec); m->graph_exec = nullptr; }
   if (m->graph) { cudaGraphDestroy(m->graph); m->graph = nullptr; }
@@ -923,6 +1012,26 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
     DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   m->flags_dirty = false;
+  return DLQ_OK;
+}
+/* read-only facts about the plan of batch N: "chain_layers" (0: no chain), "chain_pdl" (1: the cooperative chain launch also
+ * carries programmatic stream serialization), "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
+int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value) {
+  if (!m) return DLQ_ERR_ARG;
+  dlq_ctx* ctx = m->ctx;
+  DLQ_ARG(ctx, key && value && N > 0 && N <= m->max_batch, "null pointer or batch outside 1..max_batch");
+  (void)dlq_resnet18_launches_for_batch(m, N);      // plans the batch if it is not planned yet
+  auto it = m->plans.find(N);
+  DLQ_ARG(ctx, it != m->plans.end(), "batch could not be planned");
+  const dlq_resnet18::Plan& P = *it->second;
+  const std::string k(key);
+  if (k == "chain_layers") *value = P.has_chain ? P.chain.cp.n_layers : 0;
+  else if (k == "chain_pdl") *value = P.has_chain && P.chain.pdl ? 1 : 0;
+  else if (k == "chain_cta_pairs") *value = P.has_chain ? static_cast<int>(P.chain.grid.x / 2) : 0;
+  else if (k == "chain_a_stages") *value = P.has_chain ? P.chain.cp.a_stages : 0;
+  else if (k == "chain_b_stages") *value = P.has_chain ? P.chain.cp.b_stages : 0;
+  else if (k == "flag_units") *value = P.flag_units;
+  else DLQ_ARG(ctx, false, "unknown key");
   return DLQ_OK;
 }
 /* dependency waits that timed out since creation (a lost producer; must stay 0).  Synchronises. */

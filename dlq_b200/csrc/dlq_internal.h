@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 #include "../../include/dlq.h"
-#include "conv_kernel.cuh"
+#include "conv_chain.cuh"
 
 struct dlq_ctx {
   int device = 0;
@@ -125,8 +125,19 @@ struct ConvLaunch {
 // Build the launch for conv `w` reading `in` and writing `out` (either of out.ptr / acc_out may be null).
 int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act& out, const float* alpha,
               const float* beta, const Act* residual, float res_mul, int relu, int32_t* acc_out, ConvLaunch* L,
-              const SecondConv* second = nullptr);
+              const SecondConv* second = nullptr, bool allow_resident = true);   // (false: stream the weight steps - conv chain)
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L);
+// Several planned convs as ONE persistent cooperative launch (conv_chain.cuh).  plan_chain returns DLQ_ERR_ARG (and
+// leaves ctx->err) when a layer does not have the chain's static configuration; the caller then launches them one by one.
+struct ChainLaunch {
+  ChainParams cp;
+  dim3 grid, block;
+  size_t smem = 0;
+  int fp8 = 0;
+  bool pdl = true;          // combine the cooperative launch with programmatic stream serialization (dropped if refused)
+};
+int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, ChainLaunch* out);
+int launch_chain(dlq_ctx* ctx, ChainLaunch& C);
 // dependency flags between the conv launches of one forward (conv_kernel.cuh "dependency flags"):
 int conv_flag_units(const ConvLaunch& L);                                          // counters the launch needs
 void conv_set_flags(ConvLaunch* L, unsigned int* done, unsigned int* dep_err);     // keep per-unit completion counters

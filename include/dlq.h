@@ -252,6 +252,15 @@ int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
  * items whose inputs are ready while launch L drains.  0 restores grid-level dependencies (A/B measurements); results
  * are bit-identical either way.  Synchronises. */
 int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value);
+/* Further keys: "conv_chain" (default 1): at batches above 16 the convs from "chain_start" to the last one run as ONE
+ * persistent cooperative kernel (csrc/conv_chain.cuh) whose CTA pairs walk the layers without leaving the SMs - no
+ * per-layer hand-over, no partial last waves - with the tile-level dependency flags between them.  "chain_start" is the
+ * conv index (DLQ_NUM_CONVS numbering) of a block's conv1 or conv2; default 8 = layer2.0.conv2, the first of the thirteen
+ * convs with 128 or more input channels; "chain_first_block" = b is shorthand for conv1 of block b (1..7).  A chain whose
+ * layers do not share the kernel's static tile configuration falls back to one launch per conv.  Bit-identical results. */
+/* facts about the launch plan of batch N (planned on demand): "chain_layers" (0 = one launch per conv), "chain_pdl",
+ * "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
+int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value);
 /* dependency waits that ran into the 4 s safety timeout since creation (must be 0).  Synchronises. */
 int dlq_resnet18_dep_timeouts(dlq_resnet18* m, unsigned int* count);
 /* Span stamps (measurement): with a ring of `ring_forwards` entries, every kernel of a forward records the globaltimer

@@ -208,7 +208,12 @@ def test_launch_count_and_span_stamps(ctx, model256):
     import torch
     assert model256.launches == 23
     assert model256.launches_for_batch(8) == 20 and model256.launches_for_batch(16) == 20
+    # above 16: the thirteen convs from layer2.0.conv2 on share ONE persistent launch (conv_chain.cuh)
+    assert model256.launches_for_batch(17) == 11 and model256.launches_for_batch(256) == 11
+    assert model256.plan_info(256, "chain_layers") == 13 and model256.plan_info(8, "chain_layers") == 0
+    model256.set_option("conv_chain", 0)
     assert model256.launches_for_batch(17) == 23 and model256.launches_for_batch(256) == 23
+    model256.set_option("conv_chain", 1)
     x = torch.from_numpy(synth.make_input(0, 32)).cuda()
     dl = torch.empty((32, 1000), dtype=torch.float32, device="cuda")
     model256.enable_stamps(4)
@@ -249,12 +254,18 @@ def test_tile_dependency_flags_equal_grid_dependencies(ctx, n):
     m.set_option("tile_flags", 1)
     dx = torch.from_numpy(x).cuda()
     dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
-    for rep in range(40 if n < 256 else 15):
-        dl.fill_(7.0)
+    x2 = _tile(synth.make_input(77, min(n, 32)), n)
+    want2 = _forward(ctx, m, x2)["logits"]
+    dx2 = torch.from_numpy(x2).cuda()
+    dl2 = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    ctx.sync()
+    for rep in range(40 if n < 256 else 15):        # two different batches back to back, no host synchronisation
         m.forward(dx, dl)
+        m.forward(dx2, dl2)
         if rep % 5 == 4:
             ctx.sync()
             assert np.array_equal(dl.cpu().numpy().view(np.uint32), want["logits"].view(np.uint32)), rep
+            assert np.array_equal(dl2.cpu().numpy().view(np.uint32), want2.view(np.uint32)), rep
     m.graph_capture(dx, dl)
     for rep in range(20):
         m.graph_launch()
@@ -266,6 +277,58 @@ def test_tile_dependency_flags_equal_grid_dependencies(ctx, n):
         assert np.array_equal(got2["logits"].view(np.uint32), want["logits"][:5].view(np.uint32))
         got3 = _forward(ctx, m, x)
         assert np.array_equal(got3["layer3"], want["layer3"])
+    assert m.dep_timeouts == 0
+    m.close()
+
+
+@pytest.mark.parametrize("n,start", [(17, 8), (40, 8), (256, 8), (64, 19), (33, 13), (24, 11)])
+def test_conv_chain_equals_separate_launches(ctx, n, start):
+    """the persistent multi-layer kernel (default at batches above 16) vs one launch per conv: identical checkpoints and
+    logits, stable over repeated forwards and graph replays, and - where the oracle finishes in seconds - equal to it"""
+    import torch
+    import dlq_b200
+    m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    m.set_option("chain_start", start)      # 8 = layer2.0.conv2 (default), 19 = layer4.0.conv1, 13 = layer3.0.conv1, 11 = layer2.1.conv2
+    x = _tile(synth.make_input(17, min(n, 40)), n)
+    want = _forward(ctx, m, x)
+    assert m.launches_for_batch(n) < 23, "the chain replaces several launches"
+    if n <= 40:
+        ref = orc.I8Model(synth.make_weights(0), synth.load_act_scales(0)).forward(x, checkpoints=True)
+        for k in CKPTS:
+            assert np.array_equal(want[k], ref[k]), k
+        assert np.array_equal(want["logits"].view(np.uint32), ref["logits"].view(np.uint32))
+    m.set_option("conv_chain", 0)
+    got = _forward(ctx, m, x)
+    assert m.launches_for_batch(n) == 23
+    for k in list(CKPTS) + ["logits"]:
+        assert np.array_equal(got[k], want[k]), k
+    m.set_option("conv_chain", 1)
+    dx = torch.from_numpy(x).cuda()
+    dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    # back-to-back forwards WITHOUT host synchronisation, alternating between two different batches (and two batch sizes):
+    # a consumer tile that ran ahead of its producer would pick up the other batch's activations
+    x2 = _tile(synth.make_input(99, min(n, 40)), n)
+    want2 = _forward(ctx, m, x2)
+    n3 = max(17, n // 2 + 1)
+    want3 = _forward(ctx, m, x2[:n3])["logits"]
+    dx2 = torch.from_numpy(x2).cuda()
+    dl2 = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+    dl3 = torch.empty((n3, 1000), dtype=torch.float32, device="cuda")
+    ctx.sync()
+    for rep in range(12 if n < 256 else 6):
+        m.forward(dx, dl)
+        m.forward(dx2[:n3], dl3)
+        m.forward(dx2, dl2)
+        if rep % 3 == 2:
+            ctx.sync()
+            assert np.array_equal(dl.cpu().numpy().view(np.uint32), want["logits"].view(np.uint32)), rep
+            assert np.array_equal(dl2.cpu().numpy().view(np.uint32), want2["logits"].view(np.uint32)), rep
+            assert np.array_equal(dl3.cpu().numpy().view(np.uint32), want3.view(np.uint32)), rep
+    m.graph_capture(dx, dl)
+    for rep in range(10):
+        m.graph_launch()
+    ctx.sync()
+    assert np.array_equal(dl.cpu().numpy().view(np.uint32), want["logits"].view(np.uint32))
     assert m.dep_timeouts == 0
     m.close()
 
