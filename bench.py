@@ -540,6 +540,25 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     except Exception as ex:
         e2e_u8 = {"value": None, "error": str(ex)}
 
+    # ---- A/B on this box, in this process: the conv chain (default) vs one launch per conv with grid-level dependencies
+    chain_ab = None
+    if not args.no_extras:
+        try:
+            model.set_option("conv_chain", 0)
+            ms_grid, _ = timed(lambda: model.forward(x, logits), args.steps, 3)
+            same = bool(torch.equal(logits.view(torch.int32), ref_logits.view(torch.int32)))
+            launches_grid = model.launches_for_batch(B)
+            model.set_option("conv_chain", 1)
+            ms_chain, _ = timed(lambda: model.forward(x, logits), args.steps, 3)
+            chain_ab = {"ms_per_step_chain": ms_chain / args.steps, "ms_per_step_one_launch_per_conv": ms_grid / args.steps,
+                        "launches_chain": model.launches_for_batch(B), "launches_one_per_conv": launches_grid,
+                        "chain_layers": model.plan_info(B, "chain_layers"), "logits_identical": same,
+                        "dep_timeouts": model.dep_timeouts,
+                        "how": "dlq_resnet18_set_option(conv_chain): the thirteen convs from layer2.0.conv2 on as ONE persistent "
+                               "cooperative kernel (csrc/conv_chain.cuh) vs one launch each, same process, same box"}
+        except Exception as ex:
+            chain_ab = {"error": str(ex)}
+
     # ---- sustained: the same step for >= 3 s (clocks settle to the sustained level), against the sustained peak
     sustained = None
     if not args.no_extras:
@@ -726,7 +745,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops,
                      "traffic": (traffic or {}).get("conv_family_dram_bytes_per_step"),
                      "traffic_source": (traffic or {}).get("source"),
-                     "kernel": "conv_i8_kernel<32|64|128, pair> (20 launches/step)",
+                     "kernel": "conv_i8_kernel<32|64, .> (7 launches/step) + conv_chain_kernel (13 layers, 1 launch): the 20 convs",
                      "peak_source": f"2 x bf16_tflops{'' if burst else '_sustained'} ({peak_kind}); int8 dense = 2 x bf16 on sm_100; "
                                     f"burst figure because the sampled SM clock is {sm_mhz:.0f} MHz" if burst else
                                     f"2 x bf16_tflops_sustained ({peak_kind}): sampled SM clock {sm_mhz:.0f} MHz < 1900",
@@ -746,6 +765,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                      "in_step_spans_us": rep["spans_us"],
                      "per_launch_ms_between_events": {n: round(float(v), 4) for n, v in zip(names, prof)}},
         "roofline_bw": roofline_bw,
+        "chain_ab": chain_ab,
         "sustained": sustained,
         "cpu_baseline": cpu,
         "e2e_u8": e2e_u8,

@@ -1,17 +1,18 @@
 #!/bin/bash
-# Round evidence: bench line, ncu launch list of the same command, full ncu capture of the conv launches of one step,
-# per-layer sweep, probes.  Every profiled command is first run plainly (it must exit 0 without ncu).
+# Round evidence (one gpurun call): bench line, ncu launch list of the same command, one full ncu capture of every kernel of one
+# step (conv launches + chain + bandwidth kernels), per-layer sweeps at batch 256 and 1.  Every profiled command is first run
+# plainly (it must exit 0 without ncu).
 set -u
 O=gpurun_out
-timeout 250 python bench.py --steps 50 --warmup 10 > $O/r01_bench_b256.json 2> $O/bench_err.log < /dev/null || echo "bench failed"
-timeout 100 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > /dev/null 2>&1 < /dev/null && \
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r01_ncu_launches.csv \
+R=${1:-r02}
+timeout 400 python bench.py --steps 50 --warmup 10 > $O/${R}_bench_b256.json 2> $O/bench_err.log < /dev/null || echo "bench failed"
+timeout 100 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $O/plain.log 2>&1 < /dev/null && \
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_ncu_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $O/ncu_launch.log 2>&1 < /dev/null
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv_i8 -s 60 -c 20 -o $O/r01_conv_full -f \
+# one whole forward: 11 launches behind the 5 warm-up forwards of the device-resident measurement (5 x 11 = 55 launches)
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:"conv_|maxpool_rows|stem_s2d|gap_fc" -s 55 -c 11 -o $O/${R}_step_full -f \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $O/ncu_full.log 2>&1 < /dev/null
-timeout 120 python tools/conv_sweep.py --iters 10 > $O/r01_conv_sweep.jsonl 2> $O/r01_conv_sweep.txt
-timeout 60 probe/_build/mma_rate > $O/r01_mma_rate.log 2>&1
-timeout 60 probe/_build/ldc_rate > $O/r01_ldc_rate.log 2>&1
-timeout 100 python tools/latency.py --batch 1 8 32 --iters 500 2>/dev/null | tail -1 > $O/r01_latency.json
-python tools/benchsum.py $O/r01_bench_b256.json
+timeout 120 python tools/conv_sweep.py --iters 10 > $O/${R}_conv_sweep.jsonl 2> $O/${R}_conv_sweep.txt
+timeout 120 python tools/conv_sweep.py --iters 20 --batch 1 > $O/${R}_conv_sweep_b1.jsonl 2> $O/${R}_conv_sweep_b1.txt
+timeout 100 python tools/latency.py --batch 1 8 32 --iters 500 2>/dev/null | tail -1 > $O/${R}_latency.json
 tail -3 $O/ncu_full.log
