@@ -392,6 +392,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     weights = synth.make_weights(0)
     scales = synth.load_act_scales(0)
     model = dlq_b200.ResNet18(ctx, weights, scales, B)
+    if args.chain_launch_mode:
+        model.set_option("chain_launch_mode", args.chain_launch_mode)
     names = model.LAUNCH_NAMES
     # every rank gets its own shard of the global synthetic batch (weak scaling: B images per rank)
     xh_np = synth.make_input(rank, 8)
@@ -471,7 +473,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     spans = in_step_spans(stamps, names)[2:] if stamps.shape[0] > 4 else in_step_spans(stamps, names)
     med = lambda k: float(np.median([d[k] for d in spans if k in d]))
     conv_union_ms = med("conv_union_ms")
-    period_ms = med("period_ms") if any("period_ms" in d for d in spans) else ms_st / ring
+    # (forwards that are not back to back - a host synchronisation in between - have no meaningful period)
+    periods = [d["period_ms"] for d in spans if "period_ms" in d and d["period_ms"] < 10 * step_ms]
+    period_ms = float(np.median(periods)) if periods else step_ms
     rep = sorted(spans, key=lambda d: d["conv_union_ms"])[len(spans) // 2]       # the median forward, launch by launch
 
     # ---- per-launch durations with a CUDA event between launches (forbids the overlap the step runs with)
@@ -808,6 +812,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the FP8 and batch-1 latency side measurements")
+    ap.add_argument("--chain-launch-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="launch attributes of the conv chain kernel: 0 cooperative + programmatic serialization (default), "
+                         "1 cooperative, 2 neither - for captures under ncu, which fails on cooperative cluster launches")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

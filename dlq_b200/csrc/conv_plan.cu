@@ -604,31 +604,48 @@ int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, Chai
 }
 
 int launch_chain(dlq_ctx* ctx, ChainLaunch& C) {
-  for (;;) {
+  // launch modes, tried in order from the last one that worked: 0 = cooperative + programmatic stream serialization,
+  // 1 = cooperative, 2 = neither.  Mode 2 gives no co-residency guarantee and is taken only when the driver refuses a
+  // cooperative launch (seen under the ncu profiler, which runs every kernel alone on the device anyway) and the grid is
+  // one CTA per SM of an otherwise idle device.
+  const int first_mode = C.mode;
+  for (; C.mode <= 2; ++C.mode) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = C.grid;
     cfg.blockDim = C.block;
     cfg.dynamicSmemBytes = C.smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[3];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeCooperative;       // every CTA pair resident at once
-    attr[1].val.cooperative = 1;
-    attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[2].val.programmaticStreamSerializationAllowed = 1;
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (C.mode <= 1) {
+      attr[na].id = cudaLaunchAttributeCooperative;       // every CTA pair resident at once
+      attr[na].val.cooperative = 1;
+      ++na;
+    }
+    if (C.mode == 0 && !ctx->no_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = (C.pdl && !ctx->no_pdl) ? 3 : 2;
+    cfg.numAttrs = na;
     const cudaError_t e = C.fp8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, C.cp)
                                 : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, C.cp);
-    if (e == cudaSuccess) return DLQ_OK;
-    if (cfg.numAttrs == 3) {       // cooperative + programmatic serialization refused together: keep the cooperative one
-      cudaGetLastError();
-      C.pdl = false;
-      continue;
+    if (e == cudaSuccess) {
+      if (C.mode == 2 && first_mode != 2 && !C.warned) {
+        fprintf(stderr, "[dlq] conv chain: cooperative launch refused by the driver; launched without the co-residency guarantee\n");
+        C.warned = true;
+      }
+      return DLQ_OK;
     }
-    DLQ_CUDA(ctx, e);
+    if (C.mode == 2 || (C.mode == 1 && static_cast<int>(C.grid.x) != ctx->num_sms)) DLQ_CUDA(ctx, e);
+    cudaGetLastError();
   }
+  ctx->err = "conv chain: launch failed";
+  return DLQ_ERR_CUDA;
 }
 
 int launch_conv(dlq_ctx* ctx, const ConvLaunch& L) {

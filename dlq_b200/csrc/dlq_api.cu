@@ -494,6 +494,7 @@ struct dlq_resnet18 {
   int n_flags = 0;
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
   bool conv_chain = true;     // batches above kFuseMaxBatch: the blocks from chain_first_block on as one persistent launch
+  int chain_mode0 = 0;        // first launch mode new plans try for the chain (launch_chain; option "chain_launch_mode")
   int chain_start = 8;        // conv index of the chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block; everything
                               // behind it belongs to the chain.  8 = layer2.0.conv2: the thirteen convs with 128-byte K rows
   // span stamps: ring of [forward][launch][2] globaltimer values (dlq_resnet18_enable_stamps)
@@ -668,7 +669,7 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
       }
       // (too many layers, or one without the chain's static configuration: the blocks simply stay separate launches)
       P->chain_first_conv = chain_start;
-      if (n <= kMaxChainLayers && plan_chain(ctx, layers, n, &P->chain) == DLQ_OK) P->has_chain = true;
+      if (n <= kMaxChainLayers && plan_chain(ctx, layers, n, &P->chain) == DLQ_OK) { P->has_chain = true; P->chain.mode = m->chain_mode0; }
       else if (!m->tile_flags) return build_plan_without_chain(m, N, P);
     }
   }
@@ -926,7 +927,8 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
             C->cp.layer[k].p.stamps = st_base + 2 * pos;
           }
           const int rc = launch_chain(ctx, *C);
-          P.chain.pdl = C->pdl;
+          P.chain.mode = C->mode;
+          P.chain.warned = C->warned;
           return rc;
         }
     }
@@ -993,8 +995,9 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   dlq_ctx* ctx = m->ctx;
   DLQ_ARG(ctx, key != nullptr, "null key");
   const std::string k(key);
-  DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start",
-          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start)");
+  DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start" || k == "chain_launch_mode",
+          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start | chain_launch_mode)");
+  DLQ_ARG(ctx, k != "chain_launch_mode" || (value >= 0 && value <= 2), "chain_launch_mode outside 0..2");
   DLQ_ARG(ctx, k != "chain_first_block" || (value >= 1 && value <= 7), "chain_first_block outside 1..7");
   DLQ_ARG(ctx, k != "chain_start" || (value >= 1 && value < DLQ_NUM_CONVS && (value - 1) % 3 != 2),
           "chain_start must be the index of a block's conv1 (1 + 3b) or conv2 (2 + 3b)");
@@ -1002,6 +1005,7 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   DLQ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (k == "tile_flags") m->tile_flags = value != 0;
   else if (k == "conv_chain") m->conv_chain = value != 0;
+  else if (k == "chain_launch_mode") m->chain_mode0 = value;
   else if (k == "chain_first_block") m->chain_start = 1 + 3 * value;
   else m->chain_start = value;
   m->plans.clear();
@@ -1014,8 +1018,8 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   m->flags_dirty = false;
   return DLQ_OK;
 }
-/* read-only facts about the plan of batch N: "chain_layers" (0: no chain), "chain_pdl" (1: the cooperative chain launch also
- * carries programmatic stream serialization), "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
+/* read-only facts about the plan of batch N: "chain_layers" (0: no chain), "chain_launch_mode" (0: cooperative launch with
+ * programmatic stream serialization, 1: cooperative, 2: neither - only when the driver refuses cooperative launches), "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
 int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value) {
   if (!m) return DLQ_ERR_ARG;
   dlq_ctx* ctx = m->ctx;
@@ -1026,7 +1030,7 @@ int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value) 
   const dlq_resnet18::Plan& P = *it->second;
   const std::string k(key);
   if (k == "chain_layers") *value = P.has_chain ? P.chain.cp.n_layers : 0;
-  else if (k == "chain_pdl") *value = P.has_chain && P.chain.pdl ? 1 : 0;
+  else if (k == "chain_launch_mode") *value = P.has_chain ? P.chain.mode : -1;
   else if (k == "chain_cta_pairs") *value = P.has_chain ? static_cast<int>(P.chain.grid.x / 2) : 0;
   else if (k == "chain_a_stages") *value = P.has_chain ? P.chain.cp.a_stages : 0;
   else if (k == "chain_b_stages") *value = P.has_chain ? P.chain.cp.b_stages : 0;

@@ -134,7 +134,8 @@ struct ChainLaunch {
   dim3 grid, block;
   size_t smem = 0;
   int fp8 = 0;
-  bool pdl = true;          // combine the cooperative launch with programmatic stream serialization (dropped if refused)
+  int mode = 0;             // launch attributes that worked last (launch_chain): 0 cooperative + PDL, 1 cooperative, 2 plain
+  bool warned = false;
 };
 int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, ChainLaunch* out);
 int launch_chain(dlq_ctx* ctx, ChainLaunch& C);

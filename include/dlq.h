@@ -258,7 +258,7 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value);
  * conv index (DLQ_NUM_CONVS numbering) of a block's conv1 or conv2; default 8 = layer2.0.conv2, the first of the thirteen
  * convs with 128 or more input channels; "chain_first_block" = b is shorthand for conv1 of block b (1..7).  A chain whose
  * layers do not share the kernel's static tile configuration falls back to one launch per conv.  Bit-identical results. */
-/* facts about the launch plan of batch N (planned on demand): "chain_layers" (0 = one launch per conv), "chain_pdl",
+/* facts about the launch plan of batch N (planned on demand): "chain_layers" (0 = one launch per conv), "chain_launch_mode",
  * "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
 int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value);
 /* dependency waits that ran into the 4 s safety timeout since creation (must be 0).  Synchronises. */

@@ -84,7 +84,7 @@ def main():
         ends = [b for _, _, b in rep["spans_us"]]
         print("   end      " + "  ".join(f"{n.replace('layer', 'L')}:{b:.1f}" for n, a, b in rep["spans_us"]))
     set_mode(modes[0])
-    print("dep_timeouts", m.dep_timeouts, {k: m.plan_info(B, k) for k in ("chain_layers", "chain_pdl", "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units")})
+    print("dep_timeouts", m.dep_timeouts, {k: m.plan_info(B, k) for k in ("chain_layers", "chain_launch_mode", "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units")})
 
 
 if __name__ == "__main__":
