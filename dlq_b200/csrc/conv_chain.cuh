@@ -16,19 +16,21 @@
 // Replaces the per-block launch sequence of basic_block_forward (reference runtime/infer_e2e.cu:156-203) for the blocks
 // it covers; the arithmetic of every layer is conv_i8_kernel's (same issuer, same epilogue code).
 //
-// Static configuration shared by all layers of a chain (checked by the planner): 128-byte K rows, CTA pairs
-// (cta_group::2), two 128-position tiles per item and 128-channel n-tiles (TMEM: two accumulator stages of 256
-// columns), streamed weights, no fused shortcut, no raw-accumulator output.
+// Static configuration shared by all layers of a chain (checked by the planner): one of two tile shapes - CTA pairs
+// (cta_group::2) with two 128-position tiles per item and 128-channel n-tiles (layer2..4), or single CTAs with four tiles
+// and 64-channel n-tiles (layer1) - i.e. two TMEM accumulator stages of 256 columns either way; streamed weights, no fused
+// shortcut, no raw-accumulator output.  The K-row width (64 or 128 bytes) may differ from layer to layer.
 #pragma once
 #include "conv_kernel.cuh"
 
 namespace dlq {
 
-constexpr int kMaxChainLayers = 13;
+constexpr int kMaxChainLayers = 15;
 
 struct ChainLayer {
   ConvKernelParams p;
-  int item_shift;            // CTA pair g takes the items  it = (g - item_shift) mod G, + G, ...  of this layer
+  int item_shift;            // CTA (pair) g takes the items  it = (g - item_shift) mod G, + G, ...  of this layer
+  int rowb;                  // bytes of K per A / B row of this layer: 64 or 128
   CUtensorMap tm0, tmw;      // activations (3-D), packed weight image (2-D); 64-byte aligned by their type
 };
 
@@ -44,13 +46,12 @@ static_assert(sizeof(ChainParams) <= 32000, "kernel parameters are limited to 32
 // smem layout (dynamic, 1024-aligned base):
 //   [A ring][B ring][alpha, beta: 2 * oc_max f32][epilogue staging: 16 * kEpiStageBytes][step offsets: 2 issuers]
 //   [barriers][tmem slot, dependency words]
-template <bool FP8>
+template <bool TWO, int MT, int N_TILE, bool FP8>
 __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constant__ ChainParams cp) {
-  constexpr int ROWB = 128;
-  constexpr bool TWO = true;
-  constexpr uint32_t TILE16 = kTileM * ROWB / 16;
-  constexpr int MT = 2, N_TILE = 128, ACC_STAGES = 2;
+  constexpr int ACC_STAGES = 2;
   constexpr uint32_t ACC_COLS = MT * N_TILE;
+  static_assert(ACC_COLS * ACC_STAGES == 512 && MT % 2 == 0, "two accumulator stages fill the 512 TMEM columns; one half of the tiles per issuer");
+  constexpr int ncta = TWO ? 2 : 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -76,24 +77,27 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int n_epi_warps = 8;
   constexpr int n_issuers = 2;
-  const int rank = static_cast<int>(cluster_ctarank());
-  const int gid = static_cast<int>(blockIdx.x) / 2;
-  const int G = static_cast<int>(gridDim.x) / 2;
+  const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+  const int gid = static_cast<int>(blockIdx.x) / ncta;
+  const int G = static_cast<int>(gridDim.x) / ncta;
   const bool first_grid_dep = cp.layer[0].p.n_deps == 0;     // the first layer waits for the previous kernel's grid
 
   if (threadIdx.x == 0) {
     pdl_launch_dependents();
     for (int i = 0; i < cp.a_stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], n_issuers); }
     for (int i = 0; i < cp.b_stages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_issuers); }
-    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], n_issuers); mbar_init(&acc_empty[i], n_epi_warps * 2); }
+    for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(&acc_full[i], n_issuers); mbar_init(&acc_empty[i], n_epi_warps * ncta); }
     fence_mbar_init();
     *s_dep_seq = 0u;
     for (int i = 0; i < kStoredSlots; ++i) s_stored[i] = 0u;
   }
-  if (warp == 1) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+  if (warp == 1) {
+    if (TWO) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
+  if (TWO) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   auto first_item = [&](const ChainLayer& L) { int f = (gid - L.item_shift) % G; return f < 0 ? f + G : f; };
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
       }
       for (int it = first_item(L); it < p.n_items; it += G) {
         const int sp = it / p.n_tiles;
-        const int st = 2 * sp + rank;
+        const int st = TWO ? 2 * sp + rank : sp;
         if (p.n_deps) {
           const int g0 = st * p.super_stride;
           wait_deps(p, g0, min(g0 + p.super_stride, p.total_pos) - 1, lane);
@@ -126,9 +130,15 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
           for (int s = 0; s < p.n_sub; ++s) {
             mbar_wait(&a_empty[as], aph ^ 1u);
             uint8_t* dst = sA + static_cast<size_t>(as) * a_stage_bytes;
-            if (rank == 0) mbar_expect_tx(&a_full[as], 2u * static_cast<uint32_t>(p.tma_bytes));
-            tma_load_3d_pair(dst, &L.tm0, leader_cta_addr(&a_full[as]), p.sub_c0[s], p.sub_col0[s],
-                             p.row_mul * v0 + p.sub_row_off[s] + p.sub_plane_row[s]);
+            if (TWO) {
+              if (rank == 0) mbar_expect_tx(&a_full[as], 2u * static_cast<uint32_t>(p.tma_bytes));
+              tma_load_3d_pair(dst, &L.tm0, leader_cta_addr(&a_full[as]), p.sub_c0[s], p.sub_col0[s],
+                               p.row_mul * v0 + p.sub_row_off[s] + p.sub_plane_row[s]);
+            } else {
+              mbar_expect_tx(&a_full[as], static_cast<uint32_t>(p.tma_bytes));
+              tma_load_3d(dst, &L.tm0, &a_full[as], p.sub_c0[s], p.sub_col0[s],
+                          p.row_mul * v0 + p.sub_row_off[s] + p.sub_plane_row[s]);
+            }
             if (++as == static_cast<uint32_t>(cp.a_stages)) { as = 0; aph ^= 1u; }
           }
         }
@@ -169,16 +179,22 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
             mbar_wait(&b_empty[bs], bph ^ 1u);
             uint8_t* dst = sB + static_cast<size_t>(bs) * b_stage_bytes;
             const int row0 = (nt * p.n_steps + k) * p.n_tile + rank * p.w_rows;
-            if (rank == 0) mbar_expect_tx(&b_full[bs], 2u * p.step_bytes);
-            tma_load_2d_pair(dst, &L.tmw, leader_cta_addr(&b_full[bs]), 0, row0);
+            if (TWO) {
+              if (rank == 0) mbar_expect_tx(&b_full[bs], 2u * p.step_bytes);
+              tma_load_2d_pair(dst, &L.tmw, leader_cta_addr(&b_full[bs]), 0, row0);
+            } else {
+              mbar_expect_tx(&b_full[bs], p.step_bytes);
+              tma_load_2d(dst, &L.tmw, &b_full[bs], 0, row0);
+            }
             if (++bs == static_cast<uint32_t>(cp.b_stages)) { bs = 0; bph ^= 1u; }
           }
         }
       }
     }
   } else if ((warp == 1 || warp == 3) && rank == 0) {
-    // ===================================================================== MMA issuers (rank-0 CTA): one tile each
+    // ===================================================================== MMA issuers (rank-0 CTA): half of the tiles each
     const int issuer = (warp == 1) ? 0 : 1;
+    constexpr int MY_MT = MT / 2;
     uint16_t* my_steps = s_step_a16 + issuer * (kMaxSteps + 8);
     IssuerCtx c;
     c.a_full = a_full; c.a_empty = a_empty; c.b_full = b_full; c.b_empty = b_empty; c.acc_full = acc_full; c.acc_empty = acc_empty;
@@ -188,8 +204,7 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
     c.tmem_base = tmem_base; c.acc_cols = ACC_COLS; c.n_tile = N_TILE;
     c.a_stages = cp.a_stages; c.b_stages = cp.b_stages; c.acc_stages = ACC_STAGES;
     c.fused = 0; c.first_second_step = -1; c.second_off = 0;
-    c.tile_off16 = static_cast<uint32_t>(issuer) * TILE16;
-    c.d_off = static_cast<uint32_t>(issuer) * N_TILE;
+    c.d_off = static_cast<uint32_t>(issuer * MY_MT) * N_TILE;
     c.leader = elect_one();
     c.dbg = 0;
     RingState rs;
@@ -204,7 +219,9 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
       c.n_sub = p.n_sub;
       c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles;
       c.it_begin = first_item(L); c.it_end = p.n_items; c.it_stride = G;
-      run_issuer<ROWB, 1, false, TWO, 0, FP8>(c, tt, rs);
+      c.tile_off16 = static_cast<uint32_t>(issuer * MY_MT) * static_cast<uint32_t>(kTileM * L.rowb / 16);
+      if (L.rowb == 128) run_issuer<128, MY_MT, false, TWO, 0, FP8>(c, tt, rs);
+      else run_issuer<64, MY_MT, false, TWO, 0, FP8>(c, tt, rs);
     }
   } else if (warp >= 4) {
     // ===================================================================== epilogue warps
@@ -235,8 +252,10 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+  if (TWO) cluster_sync_all();
+  if (warp == 1) {
+    if (TWO) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace dlq

@@ -498,6 +498,14 @@ static int launch_rowb(dlq_ctx* ctx, const ConvLaunch& L) {
 
 // every instantiation's dynamic shared-memory limit, once per context (= per device): no function-static state, so
 // contexts on different devices / threads are independent (dlq.h), and a cubin that does not load fails dlq_create
+namespace {
+typedef void (*ChainKernel)(const ChainParams);
+ChainKernel chain_kernel(bool two, bool fp8) {
+  if (two) return fp8 ? conv_chain_kernel<true, 2, 128, true> : conv_chain_kernel<true, 2, 128, false>;
+  return fp8 ? conv_chain_kernel<false, 4, 64, true> : conv_chain_kernel<false, 4, 64, false>;
+}
+}  // namespace
+
 template <int ROWB, bool TWO, bool FP8>
 static cudaError_t configure_t(dlq_ctx* ctx) {
   return cudaFuncSetAttribute(conv_i8_kernel<ROWB, TWO, FP8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -516,8 +524,10 @@ int configure_conv_kernels(dlq_ctx* ctx) {
   DLQ_CUDA(ctx, (configure_t<32, true, true>(ctx)));
   DLQ_CUDA(ctx, (configure_t<64, true, true>(ctx)));
   DLQ_CUDA(ctx, (configure_t<128, true, true>(ctx)));
-  DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
-  DLQ_CUDA(ctx, cudaFuncSetAttribute(conv_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ctx->smem_optin)));
+  for (int two = 0; two < 2; ++two)
+    for (int fp8 = 0; fp8 < 2; ++fp8)
+      DLQ_CUDA(ctx, cudaFuncSetAttribute(chain_kernel(two != 0, fp8 != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(ctx->smem_optin)));
   return DLQ_OK;
 }
 
@@ -548,12 +558,14 @@ int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, Chai
   ChainParams& cp = out->cp;
   memset(&cp, 0, sizeof(cp));
   out->fp8 = layers[0]->fp8;
+  out->two = layers[0]->p.two;
+  const int want_mt = out->two ? 2 : 4, want_nt = out->two ? 128 : 64;      // the two tile shapes the kernel is built for
   int a_stage = 0, b_stage = 0, oc_max = 0;
   for (int l = 0; l < n_layers; ++l) {
     const ConvLaunch& L = *layers[l];
     const ConvKernelParams& p = L.p;
-    DLQ_ARG(ctx, L.rowb == 128 && p.two == 1 && p.MT == 2 && p.n_tile == 128 && p.acc_stages == 2 && !p.fused && !p.b_resident &&
-                     !p.acc_out && L.fp8 == out->fp8 && p.alpha && p.beta && p.n_steps <= kMaxSteps,
+    DLQ_ARG(ctx, (L.rowb == 128 || L.rowb == 64) && p.two == out->two && p.MT == want_mt && p.n_tile == want_nt && p.acc_stages == 2 &&
+                     !p.fused && !p.b_resident && !p.acc_out && L.fp8 == out->fp8 && p.alpha && p.beta && p.n_steps <= kMaxSteps,
             "conv chain: a layer does not have the chain's static configuration");
     a_stage = std::max(a_stage, p.sub_bytes);
     b_stage = std::max(b_stage, static_cast<int>((p.step_bytes + 1023u) & ~1023u));
@@ -569,12 +581,13 @@ int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, Chai
   cp.a_stages = a_stages; cp.b_stages = b_stages;
   cp.a_stage_bytes = a_stage; cp.b_stage_bytes = b_stage;
   cp.oc_max = oc_max;
-  // one CTA pair per SM pair, all co-resident (the CTAs wait for each other through the dependency flags)
-  int G = ctx->num_sms / 2;
+  // one CTA (pair) per SM (pair), all co-resident (the CTAs wait for each other through the dependency flags)
+  const int ncta = out->two ? 2 : 1;
+  int G = ctx->num_sms / ncta;
   out->block = dim3(128 + 8 * 32, 1, 1);
   out->smem = 1024 + static_cast<size_t>(a_stages) * a_stage + static_cast<size_t>(b_stages) * b_stage + 2 * sizeof(float) * oc_max +
               16 * kEpiStageBytes + 2 * 2 * (kMaxSteps + 8) + 8 * (2 * a_stages + 2 * b_stages + 4) + 32;
-  {
+  if (out->two) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(2 * G), 1, 1);
     cfg.blockDim = out->block;
@@ -585,18 +598,18 @@ int plan_chain(dlq_ctx* ctx, const ConvLaunch* const* layers, int n_layers, Chai
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    const cudaError_t e = out->fp8 ? cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel<true>, &cfg)
-                                   : cudaOccupancyMaxActiveClusters(&max_clusters, conv_chain_kernel<false>, &cfg);
+    const cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, chain_kernel(true, out->fp8 != 0), &cfg);
     if (e == cudaSuccess && max_clusters > 0) G = std::min(G, max_clusters);
     else cudaGetLastError();
   }
-  out->grid = dim3(static_cast<unsigned>(2 * G), 1, 1);
+  out->grid = dim3(static_cast<unsigned>(ncta * G), 1, 1);
   long long shift = 0;
   for (int l = 0; l < n_layers; ++l) {
     ChainLayer& C = cp.layer[l];
     C.p = layers[l]->p;
     C.tm0 = layers[l]->tmap;
     C.tmw = layers[l]->tmap_w;
+    C.rowb = layers[l]->rowb;
     C.item_shift = static_cast<int>(shift % G);       // the chain's items are dealt round-robin across layer boundaries
     shift += C.p.n_items;
   }
@@ -617,9 +630,11 @@ int launch_chain(dlq_ctx* ctx, ChainLaunch& C) {
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[3];
     int na = 0;
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
-    ++na;
+    if (C.two) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
     if (C.mode <= 1) {
       attr[na].id = cudaLaunchAttributeCooperative;       // every CTA pair resident at once
       attr[na].val.cooperative = 1;
@@ -632,8 +647,7 @@ int launch_chain(dlq_ctx* ctx, ChainLaunch& C) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const cudaError_t e = C.fp8 ? cudaLaunchKernelEx(&cfg, conv_chain_kernel<true>, C.cp)
-                                : cudaLaunchKernelEx(&cfg, conv_chain_kernel<false>, C.cp);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, chain_kernel(C.two != 0, C.fp8 != 0), C.cp);
     if (e == cudaSuccess) {
       if (C.mode == 2 && first_mode != 2 && !C.warned) {
         fprintf(stderr, "[dlq] conv chain: cooperative launch refused by the driver; launched without the co-residency guarantee\n");

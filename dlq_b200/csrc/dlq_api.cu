@@ -495,8 +495,9 @@ struct dlq_resnet18 {
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
   bool conv_chain = true;     // batches above kFuseMaxBatch: the blocks from chain_first_block on as one persistent launch
   int chain_mode0 = 0;        // first launch mode new plans try for the chain (launch_chain; option "chain_launch_mode")
-  int chain_start = 8;        // conv index of the chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block; everything
-                              // behind it belongs to the chain.  8 = layer2.0.conv2: the thirteen convs with 128-byte K rows
+  bool chain_l1 = true;       // layer1's four convs as a chain of their own (option "chain_layer1")
+  int chain_start = 7;        // conv index of the main chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block;
+                              // everything behind it belongs to the chain.  7 = layer2.0.conv1: the fifteen convs of layer2..4
   // span stamps: ring of [forward][launch][2] globaltimer values (dlq_resnet18_enable_stamps)
   unsigned long long* d_stamps = nullptr;
   int stamp_ring = 0;
@@ -506,11 +507,16 @@ struct dlq_resnet18 {
     ConvLaunch L[DLQ_NUM_CONVS];
     bool fused[8] = {false};    // block b's shortcut conv runs inside L[conv1 of b]
     int flag_units = 0;         // dependency counters this plan uses
-    // blocks chain_from .. 7 run as ONE persistent cooperative launch (conv_chain.cuh); chain_slot[l] = conv index of layer l
-    bool has_chain = false;
-    int chain_first_conv = 0;   // the chain member the forward's launch order reaches first (conv1 of the first chained block)
-    ChainLaunch chain;
-    int chain_conv[kMaxChainLayers] = {0};
+    // runs of convs that go out as ONE persistent cooperative launch each (conv_chain.cuh): layer1 (single-CTA tile
+    // shape) and everything from layer2.0 on (CTA-pair shape)
+    struct Chain {
+      ChainLaunch launch;
+      int n = 0;
+      int conv[kMaxChainLayers] = {0};   // conv index of layer l of the chain
+      int first_conv = 0;                // the member the forward's launch order reaches first
+    };
+    std::vector<Chain> chains;
+    int chained_convs() const { int c = 0; for (const Chain& ch : chains) c += ch.n; return c; }
   };
   std::map<int, std::unique_ptr<Plan>> plans;
   int last_N = 0;
@@ -582,8 +588,11 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   Act cur = with_n(m->a_pool, N);
   float s_cur = S[kActStem];
   // the layers of the conv chain stream their weights (one static ring layout for every layer, conv_chain.cuh)
-  const int chain_start = (m->conv_chain && N > kFuseMaxBatch) ? m->chain_start : DLQ_NUM_CONVS;
-  auto in_chain = [&](int i) { return chain_member(chain_start, i); };
+  const bool chains_on = m->conv_chain && N > kFuseMaxBatch;
+  const int chain_start = chains_on ? m->chain_start : DLQ_NUM_CONVS;
+  const bool l1_chain = chains_on && m->chain_l1 && chain_start > 5;      // (layer1 = convs 1, 2, 4, 5)
+  auto in_l1 = [&](int i) { return l1_chain && (i == 1 || i == 2 || i == 4 || i == 5); };
+  auto in_chain = [&](int i) { return chain_member(chain_start, i) || in_l1(i); };
   for (int b = 0; b < 8; ++b) {
     const int i1 = 1 + 3 * b, i2 = 2 + 3 * b, id = 3 + 3 * b;
     Act t1 = with_n(m->a_t1[b], N), o = with_n(m->a_out[b], N);
@@ -632,9 +641,9 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
     keep(2 + 3 * b);
   }
   P->flag_units = units;
-  P->has_chain = false;
-  // (conv_add_dep ignores producers that keep no counters: without "tile_flags" only the convs of the chain depend on each
-  // other through flags, and whatever they read from before the chain is covered by the chain's one grid-level wait)
+  P->chains.clear();
+  // (conv_add_dep ignores producers that keep no counters: without "tile_flags" only the convs of the chains depend on
+  // each other through flags, and whatever a chain reads from before it is covered by its one grid-level wait)
   if (m->d_flags && units <= m->n_flags) {
     const ConvLaunch* prev_out = nullptr;      // the conv that produced this block's input (null: the max-pool)
     for (int b = 0; b < 8; ++b) {
@@ -657,21 +666,33 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
       else if (prev_out) conv_add_dep(&c2, *prev_out, 1, 0, 0);            // identity skip = the block input
       prev_out = &c2;
     }
-    if (chain_start < DLQ_NUM_CONVS) {
-      const ConvLaunch* layers[kMaxChainLayers + 3];
-      int n = 0;
-      // (the 1x1 shortcut conv goes FIRST in its block: conv2 needs its rows as residual, and behind conv1 they would be
-      // the last thing every CTA produces before conv2's first items ask for them - measured: 25 us instead of 17 for conv2)
-      for (int b = 0; b < 8 && n <= kMaxChainLayers; ++b) {
+    // ---- chains: members in execution order.  The 1x1 shortcut conv goes FIRST in its block: conv2 needs its rows as
+    // residual, and behind conv1 they would be the last thing every CTA produces before conv2's first items ask for
+    // them (measured: 25 us instead of 17 for conv2)
+    auto add_chain = [&](auto member, int first_conv) -> bool {
+      dlq_resnet18::Plan::Chain ch;
+      const ConvLaunch* layers[kMaxChainLayers];
+      for (int b = 0; b < 8; ++b) {
         const int order[3] = {3 + 3 * b, 1 + 3 * b, 2 + 3 * b};
         for (int i : order)
-          if (in_chain(i) && (i != 3 + 3 * b || kBlocks[b].down)) { P->chain_conv[std::min(n, kMaxChainLayers - 1)] = i; layers[n++] = &P->L[i]; }
+          if (member(i) && (i != 3 + 3 * b || kBlocks[b].down)) {
+            if (ch.n == kMaxChainLayers) return false;
+            ch.conv[ch.n] = i;
+            layers[ch.n++] = &P->L[i];
+          }
       }
-      // (too many layers, or one without the chain's static configuration: the blocks simply stay separate launches)
-      P->chain_first_conv = chain_start;
-      if (n <= kMaxChainLayers && plan_chain(ctx, layers, n, &P->chain) == DLQ_OK) { P->has_chain = true; P->chain.mode = m->chain_mode0; }
-      else if (!m->tile_flags) return build_plan_without_chain(m, N, P);
-    }
+      ch.first_conv = first_conv;
+      // (too many layers, or one without the chain's static configuration: they stay separate launches)
+      if (ch.n < 2 || plan_chain(ctx, layers, ch.n, &ch.launch) != DLQ_OK) return false;
+      ch.launch.mode = m->chain_mode0;
+      P->chains.push_back(ch);
+      return true;
+    };
+    bool ok = true;
+    if (l1_chain) ok = add_chain(in_l1, 1) && ok;
+    if (chain_start < DLQ_NUM_CONVS) ok = add_chain([&](int i) { return chain_member(chain_start, i); }, chain_start) && ok;
+    // a planned member that ended up outside a chain streams its weights for nothing and waits on flags: plan again plainly
+    if (!ok && !m->tile_flags) return build_plan_without_chain(m, N, P);
   }
   return DLQ_OK;
 }
@@ -871,7 +892,7 @@ int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
       std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
       if (cudaSetDevice(m->ctx->device) == cudaSuccess && build_plan(mm, N, P.get()) == DLQ_OK) it = mm->plans.emplace(N, std::move(P)).first;
     }
-    if (it != mm->plans.end() && it->second->has_chain) chained = it->second->chain.cp.n_layers - 1;
+    if (it != mm->plans.end()) chained = it->second->chained_convs() - static_cast<int>(it->second->chains.size());
   }
   return 23 - fused - chained;
 }
@@ -894,7 +915,7 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   const float* S = m->act_scale;
   // dependency counters: zero at the start of every forward - the last kernel of the previous one cleared them; only a
   // forward that failed half-way leaves them dirty
-  const bool flags_on = (m->tile_flags || P.has_chain) && m->d_flags && P.flag_units <= m->n_flags;
+  const bool flags_on = (m->tile_flags || !P.chains.empty()) && m->d_flags && P.flag_units <= m->n_flags;
   if (m->flags_dirty && m->d_flags)
     DLQ_CUDA(ctx, cudaMemsetAsync(m->d_flags, 0, static_cast<size_t>(m->n_flags) * sizeof(unsigned int), ctx->stream));
   m->flags_dirty = flags_on;
@@ -912,26 +933,25 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   // conv index i of the plan: its own launch, or - for the layers of the chain - the chain's one launch at its first layer
   auto conv = [&](int i) -> int {
     unsigned long long* sp = stamp();
-    if (P.has_chain) {
-      for (int l = 0; l < P.chain.cp.n_layers; ++l)
-        if (P.chain_conv[l] == i) {
-          if (i != P.chain_first_conv) return DLQ_OK;      // (launched once, where the forward reaches its first member)
-          if (!sp) return launch_chain(ctx, P.chain);
-          std::unique_ptr<ChainLaunch> C(new ChainLaunch(P.chain));      // (measurement only: per-layer stamp slots)
-          for (int k = 0; k < C->cp.n_layers; ++k) {
+    for (dlq_resnet18::Plan::Chain& ch : P.chains)
+      for (int l = 0; l < ch.n; ++l)
+        if (ch.conv[l] == i) {
+          if (i != ch.first_conv) return DLQ_OK;      // (launched once, where the forward reaches its first member)
+          if (!sp) return launch_chain(ctx, ch.launch);
+          std::unique_ptr<ChainLaunch> C(new ChainLaunch(ch.launch));      // (measurement only: per-layer stamp slots)
+          for (int k = 0; k < ch.n; ++k) {
             // slot of conv index j in launch order: 1 stem, then per block conv1, [downsample], conv2 behind the max-pool
-            const int j = P.chain_conv[k], b = (j - 1) / 3, r = (j - 1) % 3;
+            const int j = ch.conv[k], b = (j - 1) / 3, r = (j - 1) % 3;
             int pos = 3;
             for (int bb = 0; bb < b; ++bb) pos += kBlocks[bb].down ? 3 : 2;
             pos += r == 0 ? 0 : r == 2 ? 1 : (kBlocks[b].down ? 2 : 1);
             C->cp.layer[k].p.stamps = st_base + 2 * pos;
           }
           const int rc = launch_chain(ctx, *C);
-          P.chain.mode = C->mode;
-          P.chain.warned = C->warned;
+          ch.launch.mode = C->mode;
+          ch.launch.warned = C->warned;
           return rc;
         }
-    }
     const ConvLaunch& L0 = P.L[i];
     if (!sp) return launch_conv(ctx, L0);
     ConvLaunch L = L0;
@@ -995,8 +1015,9 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   dlq_ctx* ctx = m->ctx;
   DLQ_ARG(ctx, key != nullptr, "null key");
   const std::string k(key);
-  DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start" || k == "chain_launch_mode",
-          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start | chain_launch_mode)");
+  DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start" || k == "chain_launch_mode" ||
+                   k == "chain_layer1",
+          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start | chain_layer1 | chain_launch_mode)");
   DLQ_ARG(ctx, k != "chain_launch_mode" || (value >= 0 && value <= 2), "chain_launch_mode outside 0..2");
   DLQ_ARG(ctx, k != "chain_first_block" || (value >= 1 && value <= 7), "chain_first_block outside 1..7");
   DLQ_ARG(ctx, k != "chain_start" || (value >= 1 && value < DLQ_NUM_CONVS && (value - 1) % 3 != 2),
@@ -1006,6 +1027,7 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   if (k == "tile_flags") m->tile_flags = value != 0;
   else if (k == "conv_chain") m->conv_chain = value != 0;
   else if (k == "chain_launch_mode") m->chain_mode0 = value;
+  else if (k == "chain_layer1") m->chain_l1 = value != 0;
   else if (k == "chain_first_block") m->chain_start = 1 + 3 * value;
   else m->chain_start = value;
   m->plans.clear();
@@ -1018,7 +1040,7 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   m->flags_dirty = false;
   return DLQ_OK;
 }
-/* read-only facts about the plan of batch N: "chain_layers" (0: no chain), "chain_launch_mode" (0: cooperative launch with
+/* read-only facts about the plan of batch N: "chain_layers" (convs inside chains; 0: none), "chains" (chain launches), "chain_launch_mode" (0: cooperative launch with
  * programmatic stream serialization, 1: cooperative, 2: neither - only when the driver refuses cooperative launches), "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
 int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value) {
   if (!m) return DLQ_ERR_ARG;
@@ -1029,11 +1051,13 @@ int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value) 
   DLQ_ARG(ctx, it != m->plans.end(), "batch could not be planned");
   const dlq_resnet18::Plan& P = *it->second;
   const std::string k(key);
-  if (k == "chain_layers") *value = P.has_chain ? P.chain.cp.n_layers : 0;
-  else if (k == "chain_launch_mode") *value = P.has_chain ? P.chain.mode : -1;
-  else if (k == "chain_cta_pairs") *value = P.has_chain ? static_cast<int>(P.chain.grid.x / 2) : 0;
-  else if (k == "chain_a_stages") *value = P.has_chain ? P.chain.cp.a_stages : 0;
-  else if (k == "chain_b_stages") *value = P.has_chain ? P.chain.cp.b_stages : 0;
+  const dlq_resnet18::Plan::Chain* main_chain = P.chains.empty() ? nullptr : &P.chains.back();
+  if (k == "chain_layers") *value = P.chained_convs();
+  else if (k == "chains") *value = static_cast<int>(P.chains.size());
+  else if (k == "chain_launch_mode") *value = main_chain ? main_chain->launch.mode : -1;
+  else if (k == "chain_cta_pairs") *value = main_chain ? static_cast<int>(main_chain->launch.grid.x / 2) : 0;
+  else if (k == "chain_a_stages") *value = main_chain ? main_chain->launch.cp.a_stages : 0;
+  else if (k == "chain_b_stages") *value = main_chain ? main_chain->launch.cp.b_stages : 0;
   else if (k == "flag_units") *value = P.flag_units;
   else DLQ_ARG(ctx, false, "unknown key");
   return DLQ_OK;

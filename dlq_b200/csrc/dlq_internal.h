@@ -134,6 +134,7 @@ struct ChainLaunch {
   dim3 grid, block;
   size_t smem = 0;
   int fp8 = 0;
+  int two = 1;              // CTA pairs (layer2..4 shape) or single CTAs (layer1 shape)
   int mode = 0;             // launch attributes that worked last (launch_chain): 0 cooperative + PDL, 1 cooperative, 2 plain
   bool warned = false;
 };

@@ -208,9 +208,10 @@ def test_launch_count_and_span_stamps(ctx, model256):
     import torch
     assert model256.launches == 23
     assert model256.launches_for_batch(8) == 20 and model256.launches_for_batch(16) == 20
-    # above 16: the thirteen convs from layer2.0.conv2 on share ONE persistent launch (conv_chain.cuh)
-    assert model256.launches_for_batch(17) == 11 and model256.launches_for_batch(256) == 11
-    assert model256.plan_info(256, "chain_layers") == 13 and model256.plan_info(8, "chain_layers") == 0
+    # above 16: layer1's four convs share one persistent launch, the fifteen convs of layer2..4 another (conv_chain.cuh)
+    assert model256.launches_for_batch(17) == 6 and model256.launches_for_batch(256) == 6
+    assert model256.plan_info(256, "chain_layers") == 19 and model256.plan_info(256, "chains") == 2
+    assert model256.plan_info(8, "chain_layers") == 0
     model256.set_option("conv_chain", 0)
     assert model256.launches_for_batch(17) == 23 and model256.launches_for_batch(256) == 23
     model256.set_option("conv_chain", 1)
@@ -281,14 +282,15 @@ def test_tile_dependency_flags_equal_grid_dependencies(ctx, n):
     m.close()
 
 
-@pytest.mark.parametrize("n,start", [(17, 8), (40, 8), (256, 8), (64, 19), (33, 13), (24, 11)])
+@pytest.mark.parametrize("n,start", [(17, 7), (40, 7), (256, 7), (64, 19), (33, 13), (24, 11), (48, 8)])
 def test_conv_chain_equals_separate_launches(ctx, n, start):
     """the persistent multi-layer kernel (default at batches above 16) vs one launch per conv: identical checkpoints and
     logits, stable over repeated forwards and graph replays, and - where the oracle finishes in seconds - equal to it"""
     import torch
     import dlq_b200
     m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
-    m.set_option("chain_start", start)      # 8 = layer2.0.conv2 (default), 19 = layer4.0.conv1, 13 = layer3.0.conv1, 11 = layer2.1.conv2
+    m.set_option("chain_start", start)      # 7 = layer2.0.conv1 (default), 8 = layer2.0.conv2, 19 = layer4.0.conv1, 13 = layer3.0.conv1, ...
+    m.set_option("chain_layer1", 0 if start == 13 else 1)
     x = _tile(synth.make_input(17, min(n, 40)), n)
     want = _forward(ctx, m, x)
     assert m.launches_for_batch(n) < 23, "the chain replaces several launches"

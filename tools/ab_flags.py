@@ -12,7 +12,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 MODES = {
-    "chain": {"conv_chain": 1, "tile_flags": 0, "chain_start": 8},
+    "chain": {"conv_chain": 1, "tile_flags": 0, "chain_start": 7, "chain_layer1": 1},
+    "chain_no_l1": {"conv_chain": 1, "tile_flags": 0, "chain_start": 7, "chain_layer1": 0},
+    "chain13": {"conv_chain": 1, "tile_flags": 0, "chain_start": 8, "chain_layer1": 0},
     "chain_from_L2.1": {"conv_chain": 1, "tile_flags": 0, "chain_first_block": 3},
     "chain_from_L3": {"conv_chain": 1, "tile_flags": 0, "chain_first_block": 4},
     "grid": {"conv_chain": 0, "tile_flags": 0},
@@ -84,7 +86,7 @@ def main():
         ends = [b for _, _, b in rep["spans_us"]]
         print("   end      " + "  ".join(f"{n.replace('layer', 'L')}:{b:.1f}" for n, a, b in rep["spans_us"]))
     set_mode(modes[0])
-    print("dep_timeouts", m.dep_timeouts, {k: m.plan_info(B, k) for k in ("chain_layers", "chain_launch_mode", "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units")})
+    print("dep_timeouts", m.dep_timeouts, {k: m.plan_info(B, k) for k in ("chain_layers", "chains", "chain_launch_mode", "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units")})
 
 
 if __name__ == "__main__":
