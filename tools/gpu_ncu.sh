@@ -9,6 +9,6 @@ R=${1:-r02}
 timeout 100 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --chain-launch-mode 2 > $O/plain.log 2>&1 < /dev/null && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_ncu_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --chain-launch-mode 2 > $O/ncu_launch.log 2>&1 < /dev/null
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"conv_|maxpool_rows|stem_s2d|gap_fc" -s 55 -c 11 -o $O/${R}_step_full -f \
+timeout 900 ncu --set full --import-source on --clock-control none -k regex:"conv_|maxpool_rows|stem_s2d|gap_fc" -s 30 -c 12 -o $O/${R}_step_full -f \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --chain-launch-mode 2 > $O/ncu_full.log 2>&1 < /dev/null
 tail -4 $O/ncu_full.log; tail -2 $O/ncu_launch.log
