@@ -23,7 +23,8 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlq_b200.so")
+# (DLQ_B200_LIB: tuning tools load the `make TIMING=1` build - same ABI, per-role cycle counters and experiment switches)
+LIB_PATH = os.environ.get("DLQ_B200_LIB") or os.path.join(_HERE, "libdlq_b200.so")
 
 NUM_CONVS = 25
 NUM_ACTS = 27

@@ -115,9 +115,10 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
         atomicMin(p.stamps, gt);
       }
-      for (int it = first_item(L); it < p.n_items; it += G) {
-        const int sp = it / p.n_tiles;
-        const int st = TWO ? 2 * sp + rank : sp;
+      ItemCursor cur;
+      cur.init(first_item(L), G, p.n_tiles);
+      for (; cur.it < p.n_items; cur.next()) {
+        const int st = TWO ? 2 * cur.sp + rank : cur.sp;
         if (p.n_deps) {
           const int g0 = st * p.super_stride;
           wait_deps(p, g0, min(g0 + p.super_stride, p.total_pos) - 1, lane);
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
           if (p.n_deps) fence_proxy_async_all();
           ++seq;
           asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(s_dep_seq)), "r"(seq) : "memory");
-          const int v0 = (st * p.super_stride) / p.Wp;
+          const int v0 = div_magic(st * p.super_stride, p.Wp, p.wp_magic);
           for (int s = 0; s < p.n_sub; ++s) {
             mbar_wait(&a_empty[as], aph ^ 1u);
             uint8_t* dst = sA + static_cast<size_t>(as) * a_stage_bytes;
@@ -153,7 +154,9 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
       for (int l = 0; l < cp.n_layers; ++l) {
         const ChainLayer& L = cp.layer[l];
         const ConvKernelParams& p = L.p;
-        for (int it = first_item(L); it < p.n_items; it += G, ++k) {
+        ItemCursor cur;
+        cur.init(first_item(L), G, p.n_tiles);
+        for (; cur.it < p.n_items; cur.next(), ++k) {
           const uint32_t want = static_cast<uint32_t>(n_epi_warps) * ((k / kStoredSlots) + 1u);
           const uint32_t addr = smem_u32(s_stored + (k % kStoredSlots));
           uint32_t v;
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
           } while (v < want);
           if (p.done) {
             __threadfence();
-            atomicAdd(p.done + it / p.n_tiles, static_cast<unsigned int>(n_epi_warps));
+            atomicAdd(p.done + cur.sp, static_cast<unsigned int>(n_epi_warps));
           }
         }
       }
@@ -172,9 +175,10 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
       for (int l = 0; l < cp.n_layers; ++l) {
         const ChainLayer& L = cp.layer[l];
         const ConvKernelParams& p = L.p;
-        for (int it = first_item(L); it < p.n_items; it += G) {
-          const int sp = it / p.n_tiles;
-          const int nt = it - sp * p.n_tiles;
+        ItemCursor cur;
+        cur.init(first_item(L), G, p.n_tiles);
+        for (; cur.it < p.n_items; cur.next()) {
+          const int nt = cur.nt;
           for (int k = 0; k < p.n_steps; ++k) {
             mbar_wait(&b_empty[bs], bph ^ 1u);
             uint8_t* dst = sB + static_cast<size_t>(bs) * b_stage_bytes;
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(384, 1) conv_chain_kernel(const __grid_constan
       __syncwarp();
       c.sub_step0 = p.sub_step0;
       c.n_sub = p.n_sub;
-      c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles;
+      c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles; c.wp_magic = p.wp_magic;
       c.it_begin = first_item(L); c.it_end = p.n_items; c.it_stride = G;
       c.tile_off16 = static_cast<uint32_t>(issuer * MY_MT) * static_cast<uint32_t>(kTileM * L.rowb / 16);
       if (L.rowb == 128) run_issuer<128, MY_MT, false, TWO, 0, FP8>(c, tt, rs);

@@ -149,7 +149,7 @@ struct ConvKernelParams {
   int relu2;
   int8_t* out2;
   int out2_PR;
-  uint32_t wp_magic, pv_magic;   // floor(2^32/d)+1 for d = Wp, Pv (exact for positions < 2^24); 0 = use hardware division
+  uint32_t wp_magic, pv_magic;   // floor(2^32/d) for d = Wp, Pv (div_magic)
   int dbg;                // tuning experiments only: 1 = skip the epilogue, 2 = skip MMA issue, 4 = skip A loads
   long long* dbg_times;   // optional [gridDim.x][8] cycle counters (tuning): see conv_plan.cu
 };
@@ -177,6 +177,7 @@ struct IssuerCtx {
   int it_begin, it_end, it_stride;
   int fused, first_second_step;
   uint32_t second_off;          // accumulator column offset of the fused second conv
+  uint32_t wp_magic;            // ConvKernelParams::wp_magic
   uint32_t tile_off16;          // this issuer's first tile, in 16-byte units down the patch
   uint32_t d_off;               // this issuer's first accumulator column offset
   bool leader;
@@ -216,6 +217,29 @@ __device__ __forceinline__ void issue_step(uint32_t a_hi, uint32_t b_hi, uint32_
 // that a kernel running several layers (conv_chain.cuh) carries them from one layer to the next
 struct RingState { uint32_t as = 0, aph = 0, bs = 0, bph = 0, cs = 0, cph = 0; };
 
+// The items  it, it + G, it + 2G, ...  a CTA (pair) walks, decomposed as it = sp * n_tiles + nt (super-tile index, n-tile
+// index) without a division per item: every role used to pay one (~100 dependent cycles) per item or per pass.
+struct ItemCursor {
+  int it, sp, nt, G, dq, dr, n_tiles;
+  __device__ __forceinline__ void init(int first_it, int G_, int n_tiles_) {
+    it = first_it; G = G_; n_tiles = n_tiles_;
+    sp = first_it / n_tiles_; nt = first_it - sp * n_tiles_;
+    dq = G_ / n_tiles_; dr = G_ - dq * n_tiles_;
+  }
+  __device__ __forceinline__ void next() {
+    it += G; sp += dq; nt += dr;
+    if (nt >= n_tiles) { nt -= n_tiles; ++sp; }
+  }
+};
+
+// floor(n / d) for 0 <= n < 2^31 without a hardware division: magic = floor(2^32 / d) (0xFFFFFFFF for d = 1, see
+// conv_magic in conv_plan.cu) under-estimates the quotient by at most one, which the remainder test repairs
+__device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {
+  int q = static_cast<int>(__umulhi(static_cast<uint32_t>(n), magic));
+  if (n - q * d >= d) ++q;
+  return q;
+}
+
 template <int ROWB, int MYMT, bool RESIDENT, bool TWO, int KSEL, bool FP8, bool FUSED = false>
 __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out, RingState& rs) {
   constexpr uint32_t LAYOUT = ROWB == 128 ? UMMA_SWZ_128B : ROWB == 64 ? UMMA_SWZ_64B : UMMA_SWZ_32B;
@@ -228,10 +252,15 @@ __device__ __forceinline__ void run_issuer(const IssuerCtx& c, long long* t_out,
   uint32_t as = rs.as, aph = rs.aph, bs = rs.bs, bph = rs.bph, cs = rs.cs, cph = rs.cph;
   long long t_acc = 0, t_a = 0, t_b = 0;
   bool first_pass = true;
-  for (int it = c.it_begin; it < c.it_end; it += c.it_stride) {
-    const int sp = it / c.n_tiles;
-    const int g0 = (TWO ? 2 * sp : sp) * c.super_stride;          // (pairs: super_stride % Wp == 0, so in_patch == 0)
-    const uint32_t in_patch16 = static_cast<uint32_t>(g0 - (g0 / c.Wp) * c.Wp) * (ROWB / 16);
+  ItemCursor cur;
+  cur.init(c.it_begin, c.it_stride, c.n_tiles);
+  for (; cur.it < c.it_end; cur.next()) {
+    // offset of the super-tile's first position inside its patch (pairs: super_stride % Wp == 0, so none)
+    uint32_t in_patch16 = 0;
+    if (!TWO) {
+      const int g0 = cur.sp * c.super_stride;
+      in_patch16 = static_cast<uint32_t>(g0 - div_magic(g0, c.Wp, c.wp_magic) * c.Wp) * (ROWB / 16);
+    }
     long long tw = dbg_clock();
     if (TWO) mbar_wait_cluster(&c.acc_empty[cs], cph ^ 1u); else mbar_wait(&c.acc_empty[cs], cph ^ 1u);
     t_acc += dbg_clock() - tw;
@@ -343,9 +372,9 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // producer units [lo, hi] whose rows the consumer positions [g0, g1] need (lo > hi: none)
 __device__ __forceinline__ void dep_unit_range(const ConvKernelParams& p, const ConvDep& d, int g0, int g1, int& lo, int& hi) {
-  int va = g0 / p.Wp, vb = g1 / p.Wp;
-  int na = va / p.Pv, ra = va - na * p.Pv;
-  int nb = vb / p.Pv, rb = vb - nb * p.Pv;
+  int va = div_magic(g0, p.Wp, p.wp_magic), vb = div_magic(g1, p.Wp, p.wp_magic);
+  int na = div_magic(va, p.Pv, p.pv_magic), ra = va - na * p.Pv;
+  int nb = div_magic(vb, p.Pv, p.pv_magic), rb = vb - nb * p.Pv;
   if (ra >= p.Ho) { ++na; ra = 0; }                       // starts in the pad rows behind an image
   if (nb >= p.N) { nb = p.N - 1; rb = p.Ho - 1; }
   if (rb >= p.Ho) rb = p.Ho - 1;
@@ -414,33 +443,46 @@ struct EpiCtx {
 };
 
 __device__ __forceinline__ bool decode_pos(const ConvKernelParams& p, int g, int& n, int& r, int& x) {
-  int vrow;
-  if (p.wp_magic) {
-    vrow = static_cast<int>(__umulhi(static_cast<uint32_t>(g), p.wp_magic));
-    n = static_cast<int>(__umulhi(static_cast<uint32_t>(vrow), p.pv_magic));
-  } else {
-    vrow = g / p.Wp;
-    n = vrow / p.Pv;
-  }
+  const int vrow = div_magic(g, p.Wp, p.wp_magic);
+  n = div_magic(vrow, p.Pv, p.pv_magic);
   x = g - vrow * p.Wp;
   r = vrow - n * p.Pv;
   return (x < p.Wo) && (r < p.Ho) && (n < p.N);
 }
 
-// cp.async the 32 residual rows (64 B each) of one unit into a staging slot; rows outside the tensor are zero-filled
-__device__ __forceinline__ void epi_prefetch_res(const ConvKernelParams& p, const EpiCtx& e, int slot, int g_own, int c0) {
+// this lane's accumulator row at position g: pixel index of its output row in the (row-padded NHWC, or parity-plane) output
+// tensor and of its residual row; kInvalidPix for garbage positions (pad columns / pad rows / behind the last image)
+__device__ __forceinline__ void pos_to_pix(const ConvKernelParams& p, int g, int out_PR, uint32_t& opix, uint32_t& rpix) {
   int n, r, x;
-  const bool valid = decode_pos(p, g_own, n, r, x);
-  const uint32_t rpix = valid ? static_cast<uint32_t>((p.res_PR + n * e.res_pitch + r) * p.Wo + x) : kInvalidPix;
+  const bool valid = decode_pos(p, g, n, r, x);
+  if (p.out_planes) {       // (never combined with the fused second conv)
+    const int prow = out_PR + n * (p.Ho + out_PR) + r;
+    const int pl = ((prow & 1) << 1) | (x & 1);
+    opix = valid ? static_cast<uint32_t>((pl * p.out_rows_half + (prow >> 1)) * (p.Wo >> 1) + (x >> 1)) : kInvalidPix;
+  } else {
+    opix = valid ? static_cast<uint32_t>((out_PR + n * (p.Ho + out_PR) + r) * p.Wo + x) : kInvalidPix;
+  }
+  rpix = valid ? static_cast<uint32_t>((p.res_PR + n * (p.Ho + p.res_PR) + r) * p.Wo + x) : kInvalidPix;
+}
+
+// cp.async the 32 residual rows (64 B each) of one unit into a staging slot; rows outside the tensor are zero-filled.
+// rpix = this lane's residual pixel (pos_to_pix), chan = first channel of the unit
+__device__ __forceinline__ void epi_prefetch_res(const ConvKernelParams& p, const EpiCtx& e, int slot, uint32_t rpix, int chan) {
   uint8_t* base = e.slots + slot * kEpiStageBytes;
+  const int8_t* col = p.residual + chan + e.cq * 16;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int srow = 8 * j + e.crow;
     const uint32_t rp = __shfl_sync(0xffffffffu, rpix, srow);
     const bool ok = rp != kInvalidPix;
-    const int8_t* src = p.residual + (ok ? static_cast<size_t>(rp) * p.OC + e.n0 + c0 + e.cq * 16 : 0);
-    cp_async16_zfill(smem_u32(base + epi_stage_off(srow, e.cq)), src, ok ? 16u : 0u);
+    cp_async16_zfill(smem_u32(base + epi_stage_off(srow, e.cq)), col + (ok ? static_cast<size_t>(rp) * p.OC : 0), ok ? 16u : 0u);
   }
+}
+
+// 16-byte global store under a predicate (no branch around the address arithmetic)
+__device__ __forceinline__ void st_global_v4_if(bool ok, void* ptr, const int4& v) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v4.b32 [%1], {%2, %3, %4, %5};\n\t}"
+               :: "r"(static_cast<int>(ok)), "l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // byte K of w (value + 128, i.e. already XORed with 0x80) -> float(value), exact: 0x4B0000uu is 2^23 + uu
@@ -472,25 +514,23 @@ __device__ __forceinline__ float2 e4m3x2_to_float2(uint32_t two_bytes) {
   return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 
+// opix = this lane's output pixel per unit (pos_to_pix, computed one pass ahead by the caller); g_own is only read by the
+// raw-accumulator form
 template <bool HAS_RES, int NU, bool SAME_CB, bool ACC_OUT, bool FP8>
 __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCtx& e, const uint32_t (&taddr)[2],
-                                          const int (&c0)[2], const int (&g_own)[2], bool release_acc,
-                                          uint32_t acc_empty_addr) {
-  uint32_t opix[NU];
+                                          const int (&c0)[2], const uint32_t (&opix)[2], const int (&g_own)[2],
+                                          bool release_acc, uint32_t acc_empty_addr) {
   size_t dpix[NU];
   bool valid[NU];
 #pragma unroll
   for (int u = 0; u < NU; ++u) {
-    int n, r, x;
-    valid[u] = decode_pos(p, g_own[u], n, r, x);
-    if (p.out_planes) {       // (never combined with the fused second conv)
-      const int prow = e.out_PR + n * e.out_pitch + r;
-      const int pl = ((prow & 1) << 1) | (x & 1);
-      opix[u] = valid[u] ? static_cast<uint32_t>((pl * p.out_rows_half + (prow >> 1)) * (p.Wo >> 1) + (x >> 1)) : kInvalidPix;
-    } else {
-      opix[u] = valid[u] ? static_cast<uint32_t>((e.out_PR + n * e.out_pitch + r) * p.Wo + x) : kInvalidPix;
+    valid[u] = opix[u] != kInvalidPix;
+    dpix[u] = 0;
+    if (ACC_OUT) {
+      int n, r, x;
+      decode_pos(p, g_own[u], n, r, x);
+      dpix[u] = (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x;
     }
-    dpix[u] = ACC_OUT ? (static_cast<size_t>(n) * p.Ho + r) * p.Wo + x : 0;
   }
   uint8_t* my_row[NU];    // own staged row (row = lane); chunk q sits at my_row + ((q ^ my_swz) << 4)
   const int my_swz = (e.lane >> 1) & 3;
@@ -546,8 +586,12 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float4 al[NU], be[NU];
-      al[0] = reinterpret_cast<const float4*>(e.s_alpha + c0[0] + h * 32)[j];
-      be[0] = reinterpret_cast<const float4*>(e.s_beta + c0[0] + h * 32)[j];
+      if (dbg_flags(p.dbg) & 16) {      // (tuning: no shared-memory reads for the per-channel constants; wrong results)
+        al[0] = make_float4(0.01f, 0.02f, 0.03f, 0.04f); be[0] = make_float4(1.f, 2.f, 3.f, 4.f);
+      } else {
+        al[0] = reinterpret_cast<const float4*>(e.s_alpha + c0[0] + h * 32)[j];
+        be[0] = reinterpret_cast<const float4*>(e.s_beta + c0[0] + h * 32)[j];
+      }
       if (NU == 2) {
         if (SAME_CB) { al[NU - 1] = al[0]; be[NU - 1] = be[0]; }
         else {
@@ -589,6 +633,7 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
         asm("lop3.b32 %0, %1, %2, %3, 0x70;" : "=r"(packed[u][j]) : "r"(q), "r"(sgn), "r"(e.relu_mask));   // q & ~(sgn & mask)
       }
     }
+    if (!(dbg_flags(p.dbg) & 32))       // (tuning: 32 = no staging stores / loads, no global stores; wrong results)
 #pragma unroll
     for (int u = 0; u < NU; ++u) {
       *reinterpret_cast<int4*>(my_row[u] + (((2 * h) ^ my_swz) << 4)) =
@@ -598,8 +643,8 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
     }
   }
   __syncwarp();
-  if (e.out) {
-    // all shuffles, then all (unconditional) staged reads, then the predicated stores: no serialised
+  if (e.out && !(dbg_flags(p.dbg) & 32)) {
+    // all shuffles, then all (unconditional) staged reads, then the predicated stores (no branches): no serialised
     // shuffle -> load -> store chains
     uint32_t op[NU][4];
     int4 val[NU][4];
@@ -613,11 +658,12 @@ __device__ __forceinline__ void epi_units(const ConvKernelParams& p, const EpiCt
       for (int j = 0; j < 4; ++j)
         val[u][j] = *reinterpret_cast<const int4*>(e.slots + u * kEpiStageBytes + epi_stage_off(8 * j + e.crow, e.cq));
 #pragma unroll
-    for (int u = 0; u < NU; ++u)
+    for (int u = 0; u < NU; ++u) {
+      int8_t* col = e.out + e.n0 + c0[u] + e.cq * 16;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (op[u][j] != kInvalidPix)
-          *(reinterpret_cast<int4*>(e.out + static_cast<size_t>(op[u][j]) * p.OC + e.n0 + c0[u]) + e.cq) = val[u][j];
+        st_global_v4_if(op[u][j] != kInvalidPix, col + static_cast<size_t>(op[u][j]) * p.OC, val[u][j]);
+    }
   }
   __syncwarp();
 }
@@ -649,8 +695,9 @@ __device__ __forceinline__ void run_epilogue_items(const ConvKernelParams& p, co
   const int grp = ew >> 2;
   const int row = quarter * 32 + lane;                // accumulator row within the tile
   const bool has_res = p.residual != nullptr;
-  const int cblocks = p.n_tile >> 6;
-  const int units1 = p.MT * cblocks;                   // units of the (first) conv; the fused second conv adds as many
+  const int cshift = p.n_tile >> 7;                   // log2 of the 64-channel blocks per n-tile (n_tile is 64, 128 or 256)
+  const int cmask = (1 << cshift) - 1;
+  const int units1 = p.MT << cshift;                  // units of the (first) conv; the fused second conv adds as many
   const int n_units = units1 * (p.fused ? 2 : 1);
   const int upw = (n_units - grp + n_groups - 1) / n_groups;   // units of this warp per item: grp, grp + n_groups, ...
   const int upp = (p.acc_out || p.fused) ? 1 : 2;     // units per pass (raw-accumulator output / fused second conv: one at a time)
@@ -670,64 +717,70 @@ __device__ __forceinline__ void run_epilogue_items(const ConvKernelParams& p, co
     const int local = mt * kTileM + row;
     return local < p.super_stride ? st * p.super_stride + local : p.total_pos;
   };
-  auto prefetch_pair = [&](int it, int pi) {
-    const int sp = it / p.n_tiles;
-    const int nt = it - sp * p.n_tiles;
+  // Pass descriptors are made ONE PASS AHEAD - after a pass's stores, i.e. while the warp would otherwise only wait for
+  // the next accumulator: the output pixel of this lane's row in each unit of the pass (kept in opix_n) and, with a
+  // residual, the cp.async prefetch of the units' residual rows into the staging slots.
+  uint32_t opix_n[2] = {kInvalidPix, kInvalidPix};
+  auto prepare = [&](int sp, int nt, int pi) {
     const int st = TWO ? 2 * sp + rank : sp;
-    e.n0 = nt * p.n_tile;
+    const bool second = grp + upp * pi * n_groups >= units1;       // (a fused pass never mixes the two convs)
+    const int oPR = second ? p.out2_PR : p.out_PR;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int k = upp * pi + u;
+      opix_n[u] = kInvalidPix;
       if (u < upp && k < upw) {
-        const int unit = grp + k * n_groups;
-        const int mt = unit / cblocks, cb = unit - mt * cblocks;
-        epi_prefetch_res(p, e, u, own_pos(st, mt), cb << 6);
+        int unit = grp + k * n_groups;
+        if (second) unit -= units1;
+        uint32_t rpix;
+        pos_to_pix(p, own_pos(st, unit >> cshift), oPR, opix_n[u], rpix);
+        if (has_res) epi_prefetch_res(p, e, u, rpix, nt * p.n_tile + ((unit & cmask) << 6));
       }
     }
-    cp_async_commit();
+    if (has_res) cp_async_commit();
   };
   uint32_t cs = er.cs, cph = er.cph;
   const bool flag_mode = p.n_deps != 0;
   auto wait_dep_seq = [&](uint32_t want) {             // until the patch producer has verified `want` items of this CTA
-    if (flag_mode) {
+    if (flag_mode && has_res) {
       uint32_t v;
       do {
         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(sh.s_dep_seq)) : "memory");
       } while (v < want);
     }
   };
-  if (has_res && first_it < p.n_items && n_pairs > 0) { wait_dep_seq(er.items + 1u); prefetch_pair(first_it, 0); }
-  for (int it = first_it; it < p.n_items; it += G) {
-    const int sp = it / p.n_tiles;
-    const int nt = it - sp * p.n_tiles;
+  ItemCursor cur;
+  cur.init(first_it, G, p.n_tiles);
+  if (cur.it < p.n_items && n_pairs > 0) { wait_dep_seq(er.items + 1u); prepare(cur.sp, cur.nt, 0); }
+  while (cur.it < p.n_items) {
+    const int sp = cur.sp, nt = cur.nt;
     const int st = TWO ? 2 * sp + rank : sp;
+    cur.next();                                        // (cur is now the CTA's next item)
     const uint32_t acc_empty_addr = TWO ? leader_cta_addr(&sh.acc_empty[cs]) : smem_u32(&sh.acc_empty[cs]);
     const long long tw = dbg_clock();
     mbar_wait(&sh.acc_full[cs], cph);
     t_wait += dbg_clock() - tw;
     tc_fence_after();
     const int np = (dbg_flags(p.dbg) & 1) ? 0 : n_pairs;
+    e.n0 = nt * p.n_tile;
     for (int pi = 0; pi < np; ++pi) {
       uint32_t taddr[2];
       int c0[2], g_own[2];
+      const uint32_t opix[2] = {opix_n[0], opix_n[1]};
       const int nu = (upp == 2 && 2 * pi + 1 < upw) ? 2 : 1;
-      e.n0 = nt * p.n_tile;
       // (fused launches process one unit per pass, so a pass never mixes the two convs)
-      const int unit0 = grp + upp * pi * n_groups;
-      const bool second = unit0 >= units1;
+      const bool second = grp + upp * pi * n_groups >= units1;
       e.s_alpha = (second ? sh.s_alpha2 : sh.s_alpha) + e.n0;
       e.s_beta = (second ? sh.s_beta2 : sh.s_beta) + e.n0;
       e.out = second ? p.out2 : p.out;
-      e.out_PR = second ? p.out2_PR : p.out_PR;
-      e.out_pitch = p.Ho + e.out_PR;
       e.relu_mask = (second ? p.relu2 : p.relu) ? 0xFFFFFFFFu : 0u;
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         int unit = grp + (upp * pi + (u < nu ? u : 0)) * n_groups;
         if (second) unit -= units1;
-        const int mt = unit / cblocks, cb = unit - mt * cblocks;
-        c0[u] = cb << 6;
-        g_own[u] = own_pos(st, mt);
+        const int mt = unit >> cshift;
+        c0[u] = (unit & cmask) << 6;
+        g_own[u] = p.acc_out ? own_pos(st, mt) : 0;
         taddr[u] = tmem_base + cs * acc_cols + (second ? static_cast<uint32_t>(p.MT) * p.n_tile : 0u) +
                    static_cast<uint32_t>(mt) * p.n_tile + c0[u] + (static_cast<uint32_t>(quarter * 32) << 16);
       }
@@ -736,7 +789,7 @@ __device__ __forceinline__ void run_epilogue_items(const ConvKernelParams& p, co
         cp_async_wait_all();
         __syncwarp();
       }
-#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC, FP8>(p, e, taddr, c0, g_own, last, acc_empty_addr)
+#define DLQ_EPI(RES, NUV, SAME, ACC) epi_units<RES, NUV, SAME, ACC, FP8>(p, e, taddr, c0, opix, g_own, last, acc_empty_addr)
 #define DLQ_EPI_SHAPES(RES)                                       \
   do {                                                            \
     if (nu == 1) DLQ_EPI(RES, 1, true, false);                    \
@@ -748,10 +801,9 @@ __device__ __forceinline__ void run_epilogue_items(const ConvKernelParams& p, co
       else DLQ_EPI_SHAPES(false);
 #undef DLQ_EPI_SHAPES
 #undef DLQ_EPI
-      if (has_res) {
-        if (pi + 1 < n_pairs) prefetch_pair(it, pi + 1);
-        else if (it + G < p.n_items) { wait_dep_seq(er.items + 2u); prefetch_pair(it + G, 0); }
-      }
+      // the next pass's descriptors (and residual rows): of this item, or of the CTA's next item
+      if (pi + 1 < n_pairs) prepare(sp, nt, pi + 1);
+      else if (cur.it < p.n_items) { wait_dep_seq(er.items + 2u); prepare(cur.sp, cur.nt, 0); }
     }
     // this warp's part of the item is stored: tell the signaller (see "Producer side"; it publishes only if p.done)
     __syncwarp();
@@ -873,9 +925,10 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     if (p.n_deps == 0 && leader) pdl_wait();   // grid-level dependency: activations come from the previous kernel(s);
                                                 // everything above (and the weight loads) does not
     uint32_t seq = 0;
-    for (int it = gid; it < p.n_items; it += G) {
-      const int sp = it / p.n_tiles;
-      const int st = TWO ? 2 * sp + rank : sp;
+    ItemCursor cur;
+    cur.init(gid, G, p.n_tiles);
+    for (; cur.it < p.n_items; cur.next()) {
+      const int st = TWO ? 2 * cur.sp + rank : cur.sp;
       if (p.n_deps) {
         const int g0 = st * p.super_stride;
         wait_deps(p, g0, min(g0 + p.super_stride, p.total_pos) - 1, lane);
@@ -885,7 +938,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
         if (p.n_deps) fence_proxy_async_all();   // producer's generic-proxy stores before this thread's async-proxy (TMA) reads
         ++seq;                                   // the epilogue warps may now prefetch this item's residual rows
         asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(const_cast<uint32_t*>(s_dep_seq))), "r"(seq) : "memory");
-        const int v0 = (st * p.super_stride) / p.Wp;
+        const int v0 = div_magic(st * p.super_stride, p.Wp, p.wp_magic);
         for (int s = 0; s < p.n_sub; ++s) {
           const long long tw = dbg_clock();
           mbar_wait(&a_empty[as], aph ^ 1u);
@@ -921,7 +974,9 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     if (!b_leader && lane == sig_lane && p.done) {
       // ------------------------------------------------------------------- signaller (see "Producer side")
       uint32_t k = 0;
-      for (int it = gid; it < p.n_items; it += G, ++k) {
+      ItemCursor cur;
+      cur.init(gid, G, p.n_tiles);
+      for (; cur.it < p.n_items; cur.next(), ++k) {
         const uint32_t want = static_cast<uint32_t>(n_epi_warps) * ((k / kStoredSlots) + 1u);
         const uint32_t addr = smem_u32(s_stored + (k % kStoredSlots));
         uint32_t v;
@@ -929,17 +984,18 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
           asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
         } while (v < want);
         __threadfence();
-        atomicAdd(p.done + it / p.n_tiles, static_cast<unsigned int>(n_epi_warps));
+        atomicAdd(p.done + cur.sp, static_cast<unsigned int>(n_epi_warps));
       }
     }
     if (b_leader) {
       uint32_t bs = 0, bph = 0;
       bool first = true;
-      for (int it = gid; it < p.n_items; it += G) {
+      ItemCursor cur;
+      cur.init(gid, G, p.n_tiles);
+      for (; cur.it < p.n_items; cur.next()) {
         if (p.b_resident && !first) break;   // resident weights: loaded once
         first = false;
-        const int sp = it / p.n_tiles;
-        const int nt = it - sp * p.n_tiles;
+        const int nt = cur.nt;
         for (int k = 0; k < p.n_steps; ++k) {
           mbar_wait(&b_empty[bs], bph ^ 1u);
           uint8_t* dst = sB + static_cast<size_t>(bs) * b_stage_bytes;
@@ -966,7 +1022,7 @@ conv_i8_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ 
     c.sA_u32 = smem_u32(sA); c.sB_u32 = smem_u32(sB); c.a_stage16 = a_stage_bytes >> 4; c.b_stage16 = b_stage_bytes >> 4;
     c.tmem_base = tmem_base; c.acc_cols = acc_cols; c.n_tile = static_cast<uint32_t>(p.n_tile);
     c.n_sub = p.n_sub; c.a_stages = p.a_stages; c.b_stages = p.b_stages; c.acc_stages = p.acc_stages;
-    c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles;
+    c.Wp = p.Wp; c.super_stride = p.super_stride; c.n_tiles = p.n_tiles; c.wp_magic = p.wp_magic;
     c.it_begin = gid; c.it_end = p.n_items; c.it_stride = G;
     c.fused = p.fused; c.first_second_step = p.first_second_step;
     c.second_off = static_cast<uint32_t>(p.MT) * p.n_tile;

@@ -342,13 +342,10 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const long long last_valid = (static_cast<long long>(in.N - 1) * p.Pv + (p.Ho - 1)) * p.Wp + (p.Wo - 1);
   p.num_super = static_cast<int>(last_valid / p.super_stride) + 1;
   p.n_items = ((p.num_super + ncta - 1) / ncta) * n_tiles;
-  // epilogue position decode by multiply-high instead of division: exact while positions < 2^24 and divisors <= 256
-  // (floor(2^32/d)+1; the kernel falls back to hardware division when the magics are 0)
-  p.wp_magic = p.pv_magic = 0;
-  if (total_pos + 4LL * MT * kTileM < (1LL << 24) && p.Wp >= 2 && p.Wp <= 256 && p.Pv >= 2 && p.Pv <= 256) {
-    p.wp_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Wp)) + 1u;
-    p.pv_magic = static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(p.Pv)) + 1u;
-  }
+  // position decode by multiply-high instead of division (div_magic in conv_kernel.cuh): floor(2^32 / d)
+  auto conv_magic = [](int d) { return d <= 1 ? 0xFFFFFFFFu : static_cast<uint32_t>((1ULL << 32) / static_cast<unsigned>(d)); };
+  p.wp_magic = conv_magic(p.Wp);
+  p.pv_magic = conv_magic(p.Pv);
 
   // ---- epilogue
   p.alpha = alpha;
