@@ -495,7 +495,11 @@ maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int
   __syncthreads();
   pdl_wait();          // the stem conv's output must be complete before the first slab load
   // slab of tile t: input rows [2*oh0 - 1, 2*oh0 + 2*TR - 1] clipped to the image; slot r of the buffer holds row 2*oh0-1+r
-  auto issue = [&](int t, int stage) {
+  // Tiles are walked from the LAST image backwards: the producer (the stem conv) wrote the images in order, so the
+  // newest ones are the part of its 0.8 MB/image output that may still be in the 126 MB L2 when this kernel starts
+  // (measured: 51 vs 53 us at batch 256)
+  auto issue = [&](int rt, int stage) {
+    const int t = n_tiles - 1 - rt;
     const int n = t / tiles_per_img, oh0 = (t - n * tiles_per_img) * TR;
     const int ih_lo = max(2 * oh0 - 1, 0), ih_hi = min(2 * oh0 + 2 * TR - 1, H - 1);
     const size_t prow = static_cast<size_t>(PRi) + static_cast<size_t>(n) * (H + PRi) + ih_lo;
@@ -509,12 +513,13 @@ maxpool_rows_kernel(const int8_t* __restrict__ in, int8_t* __restrict__ out, int
   int k = 0;
   if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < n_tiles) issue(blockIdx.x, 0);
   const S16Pair kMin = {0xFF80FF80u, 0xFF80FF80u};
-  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+  for (int rt = blockIdx.x; rt < n_tiles; rt += gridDim.x, ++k) {
     const int stage = k & 1;
-    const int tn = t + gridDim.x;
+    const int tn = rt + gridDim.x;
     if (threadIdx.x == 0 && tn < n_tiles) issue(tn, stage ^ 1);   // the other buffer was released by the barrier below
     mbar_wait(&full[stage], ph[stage]);
     ph[stage] ^= 1u;
+    const int t = n_tiles - 1 - rt;
     const int n = t / tiles_per_img, oh0 = (t - n * tiles_per_img) * TR;
     const uint8_t* slab = pool_smem + stage * slab_bytes;
     const int ih_base = 2 * oh0 - 1;
