@@ -494,6 +494,8 @@ struct dlq_resnet18 {
   int n_flags = 0;
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
   bool conv_chain = true;     // batches above kFuseMaxBatch: the blocks from chain_first_block on as one persistent launch
+  int chain_min_batch = 17;   // smallest batch planned with chains (option "chain_min_batch"); below it: one launch per conv,
+                              // shortcut convs fused into conv1
   int chain_mode0 = 0;        // first launch mode new plans try for the chain (launch_chain; option "chain_launch_mode")
   bool chain_l1 = true;       // layer1's four convs as a chain of their own (option "chain_layer1")
   int chain_start = 7;        // conv index of the main chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block;
@@ -588,7 +590,7 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   Act cur = with_n(m->a_pool, N);
   float s_cur = S[kActStem];
   // the layers of the conv chain stream their weights (one static ring layout for every layer, conv_chain.cuh)
-  const bool chains_on = m->conv_chain && N > kFuseMaxBatch;
+  const bool chains_on = m->conv_chain && N >= m->chain_min_batch;
   const int chain_start = chains_on ? m->chain_start : DLQ_NUM_CONVS;
   const bool l1_chain = chains_on && m->chain_l1 && chain_start > 5;      // (layer1 = convs 1, 2, 4, 5)
   auto in_l1 = [&](int i) { return l1_chain && (i == 1 || i == 2 || i == 4 || i == 5); };
@@ -599,7 +601,7 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
     // Fusing the shortcut into conv1 saves a launch and a second pass over the input, but forces one tile per
     // item (two accumulator blocks per tile in TMEM): it wins at small batches (latency), loses at large ones.
     const int fuse_max = dlq_dbg_env("DLQ_DBG_FUSE_MAX") ? atoi(dlq_dbg_env("DLQ_DBG_FUSE_MAX")) : kFuseMaxBatch;   // (tuning)
-    P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= fuse_max;
+    P->fused[b] = kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= fuse_max && !chains_on;
     if (P->fused[b]) {
       SecondConv sc;
       sc.alpha = m->d_alpha[id]; sc.beta = m->d_beta[id]; sc.relu = 0; sc.out = with_n(m->a_ds[b], N);
@@ -882,8 +884,6 @@ int dlq_resnet18_launches(const dlq_resnet18* m) {
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
   if (!m || N <= 0) return 0;
   int fused = 0;
-  for (int b = 0; b < 8; ++b)
-    if (kBlocks[b].down && m->fuse_ds && m->conv_fused[b] && N <= kFuseMaxBatch) ++fused;
   int chained = 0;       // convs that share the one chain launch (conv_chain.cuh)
   if (N <= m->max_batch) {
     dlq_resnet18* mm = const_cast<dlq_resnet18*>(m);      // (the plan cache is logically mutable)
@@ -892,7 +892,10 @@ int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
       std::unique_ptr<dlq_resnet18::Plan> P(new dlq_resnet18::Plan());
       if (cudaSetDevice(m->ctx->device) == cudaSuccess && build_plan(mm, N, P.get()) == DLQ_OK) it = mm->plans.emplace(N, std::move(P)).first;
     }
-    if (it != mm->plans.end()) chained = it->second->chained_convs() - static_cast<int>(it->second->chains.size());
+    if (it != mm->plans.end()) {
+      chained = it->second->chained_convs() - static_cast<int>(it->second->chains.size());
+      for (int b = 0; b < 8; ++b) fused += it->second->fused[b] ? 1 : 0;
+    }
   }
   return 23 - fused - chained;
 }
@@ -1016,8 +1019,9 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   DLQ_ARG(ctx, key != nullptr, "null key");
   const std::string k(key);
   DLQ_ARG(ctx, k == "tile_flags" || k == "conv_chain" || k == "chain_first_block" || k == "chain_start" || k == "chain_launch_mode" ||
-                   k == "chain_layer1",
-          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start | chain_layer1 | chain_launch_mode)");
+                   k == "chain_layer1" || k == "chain_min_batch",
+          "unknown option (tile_flags | conv_chain | chain_first_block | chain_start | chain_layer1 | chain_launch_mode | chain_min_batch)");
+  DLQ_ARG(ctx, k != "chain_min_batch" || value >= 1, "chain_min_batch must be >= 1");
   DLQ_ARG(ctx, k != "chain_launch_mode" || (value >= 0 && value <= 2), "chain_launch_mode outside 0..2");
   DLQ_ARG(ctx, k != "chain_first_block" || (value >= 1 && value <= 7), "chain_first_block outside 1..7");
   DLQ_ARG(ctx, k != "chain_start" || (value >= 1 && value < DLQ_NUM_CONVS && (value - 1) % 3 != 2),
@@ -1028,6 +1032,7 @@ int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value) {
   else if (k == "conv_chain") m->conv_chain = value != 0;
   else if (k == "chain_launch_mode") m->chain_mode0 = value;
   else if (k == "chain_layer1") m->chain_l1 = value != 0;
+  else if (k == "chain_min_batch") m->chain_min_batch = value;
   else if (k == "chain_first_block") m->chain_start = 1 + 3 * value;
   else m->chain_start = value;
   m->plans.clear();

@@ -14,13 +14,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(batch: int, iters: int):
+def measure(batch: int, iters: int, chain_min_batch=None):
     import torch
     import dlq_b200
     from dlq_b200 import synth
     ctx = dlq_b200.Context(0)
     stream = torch.cuda.ExternalStream(ctx.stream)
     m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), batch)
+    if chain_min_batch is not None:
+        m.set_option("chain_min_batch", chain_min_batch)
     x = torch.from_numpy(synth.make_input(0, batch)).cuda()
     ref = torch.empty((batch, 1000), dtype=torch.float32, device="cuda")
     out = torch.zeros((batch, 1000), dtype=torch.float32, device="cuda")
@@ -47,7 +49,7 @@ def measure(batch: int, iters: int):
     m.close()
     ctx.close()
     q = lambda v: {"median_us": float(np.median(v)), "p99_us": float(np.percentile(v, 99)), "mean_us": float(v.mean())}
-    return {"batch": batch, "iters": iters, "graph": q(g), "stream_launches": q(s), "graph_equals_stream": same,
+    return {"batch": batch, "iters": iters, "chain_min_batch": chain_min_batch, "graph": q(g), "stream_launches": q(s), "graph_equals_stream": same,
             "images_per_s_graph": batch / (np.median(g) * 1e-6)}
 
 
@@ -55,6 +57,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, nargs="+", default=[1])
     ap.add_argument("--iters", type=int, default=1000)
+    ap.add_argument("--chain-min-batch", type=int, default=None, help="plan batches >= this with the persistent conv chains")
     a = ap.parse_args()
     print(json.dumps({"config": "ResNet-18 INT8 latency, device-resident input, CUDA graph replay",
-                      "results": [measure(b, a.iters) for b in a.batch]}))
+                      "results": [measure(b, a.iters, a.chain_min_batch) for b in a.batch]}))
