@@ -493,6 +493,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     burst = sm_mhz >= 1900.0
     peak_tops = 2.0 * float(peaks["bf16_tflops"] if burst else peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     achieved = CONV_GOP_PER_IMG * B / (conv_union_ms * 1e-3) / 1e3      # TOP/s
+    n_chain_layers, n_chains = model.plan_info(B, "chain_layers"), model.plan_info(B, "chains")
+    conv_kernels_desc = (f"the 20 convs: conv_i8_kernel ({20 - n_chain_layers} launch(es)/step: the stem"
+                         f"{'' if n_chain_layers >= 19 else ' and the convs outside the chains'}) + conv_chain_kernel "
+                         f"({n_chains} launch(es)/step running {n_chain_layers} layers: layer1 as a single-CTA chain, layer2..4 as a CTA-pair chain)")
     # the tcgen05 kind::i8 issue rate this repo measured on a B200 (probe/mma_rate.cu): M=256 N=256 K=32 per 128.1 clk
     probe_mac_clk_sm = 256 * 256 * 32 / 128.1 / 2
     probe_tops = probe_mac_clk_sm * 2 * 148 * (sm_mhz or 1965.0) * 1e6 / 1e12
@@ -749,7 +753,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TFLOP/s", "frac": achieved / peak_tops,
                      "traffic": (traffic or {}).get("conv_family_dram_bytes_per_step"),
                      "traffic_source": (traffic or {}).get("source"),
-                     "kernel": "conv_i8_kernel<32|64, .> (7 launches/step) + conv_chain_kernel (13 layers, 1 launch): the 20 convs",
+                     "kernel": conv_kernels_desc,
                      "peak_source": f"2 x bf16_tflops{'' if burst else '_sustained'} ({peak_kind}); int8 dense = 2 x bf16 on sm_100; "
                                     f"burst figure because the sampled SM clock is {sm_mhz:.0f} MHz" if burst else
                                     f"2 x bf16_tflops_sustained ({peak_kind}): sampled SM clock {sm_mhz:.0f} MHz < 1900",
