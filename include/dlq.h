@@ -244,13 +244,19 @@ int dlq_resnet18_submit_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int 
 int dlq_resnet18_wait(dlq_resnet18* m);
 /* profile slots of one forward (dlq_resnet18_profile / _read_stamps): 23 = quantise, 20 convs, max-pool, GAP+FC */
 int dlq_resnet18_launches(const dlq_resnet18* m);
-/* kernels a forward of batch N really launches: 23, or 20 when the three 1x1 shortcut convs ride on conv1's launch
- * (N <= 16) */
+/* kernels a forward of batch N really launches: 6 above batch 16 (quantise, stem conv, max-pool, the layer1 chain, the
+ * layer2..4 chain, GAP+FC), 20 at batch <= 16 (the three 1x1 shortcut convs ride on conv1's launch), 23 with the chains
+ * switched off */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
-/* Option "tile_flags" (default 0): consecutive conv launches of a forward depend on each other tile by tile, through
- * completion counters in device memory, instead of grid by grid (griddepcontrol.wait): CTAs of launch L+1 start on the
- * items whose inputs are ready while launch L drains.  0 restores grid-level dependencies (A/B measurements); results
- * are bit-identical either way.  Synchronises. */
+/* Plan options (A/B measurements and tools; results are bit-identical whatever their values).  Synchronises, drops the
+ * cached plans and any captured graph.
+ *   "conv_chain" (1)        layer1's four convs and the fifteen convs of layer2..4 as two persistent cooperative launches
+ *                           (csrc/conv_chain.cuh) for batches >= "chain_min_batch"; 0: one launch per conv
+ *   "chain_min_batch" (17)  smallest batch planned with chains (measured: at batch 1 they cost 202 vs 186 us per forward)
+ *   "chain_layer1" (1), "chain_start" (7) / "chain_first_block"   which convs the chains cover
+ *   "chain_launch_mode" (0) 0 cooperative + programmatic stream serialization, 1 cooperative, 2 neither (profilers)
+ *   "tile_flags" (0)        also between SEPARATE conv launches: consumers wait for the completion counters of the producer
+ *                           units their rows touch instead of for the producer's grid (griddepcontrol.wait) */
 int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value);
 /* Further keys: "conv_chain" (default 1): at batches above 16 the convs from "chain_start" to the last one run as ONE
  * persistent cooperative kernel (csrc/conv_chain.cuh) whose CTA pairs walk the layers without leaving the SMs - no
