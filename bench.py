@@ -769,6 +769,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                        "frac": achieved / probe_tops,
                                        "source": "probe/mma_rate.cu on a B200 (profiles/r01_mma_rate.log): cta_group::2 "
                                                  "M=256 N=256 K=32 kind::i8 issues every 128.1 clk"},
+                     "frac_of_vendor_dense_spec": {"peak_tops": 4500.0, "frac": achieved / 4500.0,
+                                                   "note": "NVIDIA's dense INT8 figure for B200 (SURVEY 8d asks for both denominators)"},
                      "hbm_gbs_conv": CONV_BYTES_PER_IMG * B / (conv_union_ms * 1e-3) / 1e9,
                      "in_step_spans_us": rep["spans_us"],
                      "per_launch_ms_between_events": {n: round(float(v), 4) for n, v in zip(names, prof)}},
