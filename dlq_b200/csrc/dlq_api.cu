@@ -994,10 +994,11 @@ static int forward_impl(dlq_resnet18* m, const float* x, int N, float* logits, c
   const float s_over_hw = static_cast<float>(static_cast<double>(S[act_out(7)]) / static_cast<double>(last.H * last.W));
   unsigned int* zero = flags_on ? m->d_flags : nullptr;
   const int n_zero = flags_on ? P.flag_units : 0;
+  unsigned long long* tail_stamp = stamp();
   rc = m->fp8 ? gap_fc_act_e4m3(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000,
-                                m->d_gap_q, logits, zero, n_zero)
+                                m->d_gap_q, logits, tail_stamp, zero, n_zero)
               : gap_fc_act(ctx, last, s_over_hw, inv_scale(S[kActGap]), m->d_fc_w, m->d_fc_scale, m->d_fc_bias, 1000, m->d_gap_q,
-                           logits, stamp(), zero, n_zero);
+                           logits, tail_stamp, zero, n_zero);
   if (rc != DLQ_OK) return rc;
   if ((rc = mark()) != DLQ_OK) return rc;
   m->flags_dirty = false;

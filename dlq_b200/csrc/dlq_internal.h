@@ -164,8 +164,8 @@ int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_s
                unsigned long long* stamp = nullptr, unsigned int* zero = nullptr, int n_zero = 0);
 
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits,
-                    unsigned int* zero = nullptr, int n_zero = 0);
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned long long* stamp,
+                    unsigned int* zero, int n_zero);
 
 // dlq_api.cu: per-row symmetric quantisation of a [rows, K] fp32 matrix (QUANT_SPEC 1 / 6), host
 void quantize_rows(const float* w, int rows, int K, std::vector<int8_t>& q, std::vector<float>& s);

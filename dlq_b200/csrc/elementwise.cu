@@ -345,34 +345,81 @@ __global__ void dequantize_e4m3_f32_kernel(const uint8_t* __restrict__ q, size_t
 // fp32 in pixel order, scaled, quantised to E4M3; logits[o] = fmaf(sum_c float(g[c]) * float(w[o][c]), scale[o], bias[o])
 // with the dot product accumulated in fp32 in channel order.  Weights in the int8 kernel's transposed image
 // [C/16][1024][16 B].
+// A CTA handles kE4m3Imgs images and one of kE4m3OSplit slices of the outputs (as gap_fc_kernel: the FC weights a CTA
+// streams from L2, and their E4M3 -> float decoding, then serve every image of the CTA).  The FP32 sums keep the
+// oracle's order (pixels in raster order, channels k = 0..C-1), so the result does not depend on the decomposition.
+constexpr int kE4m3Imgs = 2;      // (the FC loop below is written for two)
+constexpr int kE4m3OSplit = 2;
 __global__ void __launch_bounds__(512)
 gap_fc_e4m3_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, int PR, float scale_over_hw,
                    float inv_gap_scale, const int8_t* __restrict__ fc_wT, const float* __restrict__ fc_scale,
                    const float* __restrict__ fc_bias, int O, int8_t* __restrict__ gap_q, float* __restrict__ logits,
-                   unsigned int* __restrict__ zero, int n_zero) {
-  extern __shared__ float gq_s[];     // [C] dequantised (unit-scale) gap values
-  const int n = blockIdx.x;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * blockDim.x) zero[i] = 0u;   // (as gap_fc_kernel)
-  const uint8_t* img = reinterpret_cast<const uint8_t*>(in) + (static_cast<size_t>(PR) + static_cast<size_t>(n) * (H + PR)) * W * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s = 0.f;
-    for (int px = 0; px < H * W; ++px) s = __fadd_rn(s, e4m3_to_float(img[static_cast<size_t>(px) * C + c]));
-    const uint8_t q = float_to_e4m3(__fmul_rn(__fmul_rn(s, scale_over_hw), inv_gap_scale));
-    if (gap_q) gap_q[static_cast<size_t>(n) * C + c] = static_cast<int8_t>(q);
-    gq_s[c] = e4m3_to_float(q);
+                   unsigned long long* stamp, unsigned int* __restrict__ zero, int n_zero) {
+  extern __shared__ float gq_s[];     // [imgs][C] dequantised (unit-scale) gap values
+  stamp_entry(stamp);
+  const int n0 = blockIdx.x * kE4m3Imgs;
+  const int nimg = min(kE4m3Imgs, N - n0);
+  pdl_wait();
+  // the last conv grid has completed: clear this forward's dependency counters for the next one (as gap_fc_kernel)
+  for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * gridDim.y * blockDim.x)
+    zero[i] = 0u;
+  // GAP: thread = (image, 16-channel group); the pixels' 16-byte loads are independent (seven in flight), the FP32
+  // additions of a channel stay in raster order
+  const int cv = C / 16;
+  for (int i = threadIdx.x; i < nimg * cv; i += blockDim.x) {
+    const int im = i / cv, cg = i - im * cv;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) +
+                         (static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR)) * W * C + cg * 16;
+    float s[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[j] = 0.f;
+#pragma unroll 7
+    for (int px = 0; px < H * W; ++px) {
+      const int4 v = __ldg(reinterpret_cast<const int4*>(src + static_cast<size_t>(px) * C));
+      const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s[j] = __fadd_rn(s[j], e4m3_to_float(static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)))));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int c = cg * 16 + j;
+      const uint8_t q = float_to_e4m3(__fmul_rn(__fmul_rn(s[j], scale_over_hw), inv_gap_scale));
+      if (gap_q && blockIdx.y == 0) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
+      gq_s[c * kE4m3Imgs + im] = e4m3_to_float(q);      // [C][imgs]: one shared load per channel serves the CTA's images
+    }
   }
+  if (nimg < kE4m3Imgs)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) gq_s[c * kE4m3Imgs + kE4m3Imgs - 1] = 0.f;     // (odd batch: unused slot)
   __syncthreads();
-  for (int o = threadIdx.x; o < O; o += blockDim.x) {
-    float acc = 0.f;
-    for (int kb = 0; kb < C / 16; ++kb) {
+  if (!logits) { stamp_exit(stamp); return; }
+  const int o_per = (O + static_cast<int>(gridDim.y) - 1) / static_cast<int>(gridDim.y);
+  const int o_end = min(O, (static_cast<int>(blockIdx.y) + 1) * o_per);
+  for (int o = static_cast<int>(blockIdx.y) * o_per + threadIdx.x; o < o_end; o += blockDim.x) {
+    float acc[kE4m3Imgs];
+#pragma unroll
+    for (int im = 0; im < kE4m3Imgs; ++im) acc[im] = 0.f;
+#pragma unroll 4
+    for (int kb = 0; kb < C / 16; ++kb) {      // (unrolled: the weight loads of four steps are in flight together)
       const int4 wv = __ldg(reinterpret_cast<const int4*>(fc_wT) + static_cast<size_t>(kb) * 1024 + o);
       const uint32_t ww[4] = {(uint32_t)wv.x, (uint32_t)wv.y, (uint32_t)wv.z, (uint32_t)wv.w};
+      // weights decoded two at a time (cvt e4m3x2 -> f16x2 -> f32, exact); the FMAs stay in channel order
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        acc = __fmaf_rn(gq_s[kb * 16 + j], e4m3_to_float(static_cast<uint8_t>(ww[j >> 2] >> (8 * (j & 3)))), acc);
+      for (int jj = 0; jj < 8; ++jj) {
+        const float2 wf = e4m3x2_to_float2((ww[jj >> 1] >> (16 * (jj & 1))) & 0xFFFFu);
+        const float2 g0 = reinterpret_cast<const float2*>(gq_s)[kb * 16 + 2 * jj];
+        const float2 g1 = reinterpret_cast<const float2*>(gq_s)[kb * 16 + 2 * jj + 1];
+        acc[0] = __fmaf_rn(g0.x, wf.x, acc[0]);
+        acc[1] = __fmaf_rn(g0.y, wf.x, acc[1]);
+        acc[0] = __fmaf_rn(g1.x, wf.y, acc[0]);
+        acc[1] = __fmaf_rn(g1.y, wf.y, acc[1]);
+      }
     }
-    logits[static_cast<size_t>(n) * O + o] = __fmaf_rn(acc, fc_scale[o], fc_bias[o]);
+    const float sc = fc_scale[o], bi = fc_bias[o];
+#pragma unroll
+    for (int im = 0; im < kE4m3Imgs; ++im)
+      if (im < nimg) logits[static_cast<size_t>(n0 + im) * O + o] = __fmaf_rn(acc[im], sc, bi);
   }
+  stamp_exit(stamp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -898,13 +945,13 @@ int configure_elementwise_kernels(dlq_ctx* ctx) {
   return DLQ_OK;
 }
 int gap_fc_act_e4m3(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
-                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned int* zero,
-                    int n_zero) {
+                    const float* fc_scale, const float* fc_bias, int O, int8_t* gap_q, float* logits, unsigned long long* stamp,
+                    unsigned int* zero, int n_zero) {
   DLQ_ARG(ctx, in.C % 16 == 0 && O <= 1024, "gap/fc geometry");
-  gap_fc_e4m3_kernel<<<in.N, 512, in.C * sizeof(float), ctx->stream>>>(in.ptr, in.N, in.H, in.W, in.C, in.PR, scale_over_hw,
-                                                                     inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits,
-                                                                     zero, n_zero);
-  DLQ_CUDA(ctx, cudaGetLastError());
+  const int blocks = (in.N + kE4m3Imgs - 1) / kE4m3Imgs;
+  DLQ_CUDA(ctx, launch_pdl(ctx, gap_fc_e4m3_kernel, dim3(blocks, logits ? kE4m3OSplit : 1), dim3(512),
+                           static_cast<size_t>(kE4m3Imgs) * in.C * sizeof(float), static_cast<const int8_t*>(in.ptr), in.N, in.H, in.W, in.C,
+                           in.PR, scale_over_hw, inv_gap_scale, fc_w, fc_scale, fc_bias, O, gap_q, logits, stamp, zero, n_zero));
   return DLQ_OK;
 }
 int gap_fc_act(dlq_ctx* ctx, const Act& in, float scale_over_hw, float inv_gap_scale, const int8_t* fc_w,
