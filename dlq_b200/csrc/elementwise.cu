@@ -346,8 +346,9 @@ __global__ void dequantize_e4m3_f32_kernel(const uint8_t* __restrict__ q, size_t
 // with the dot product accumulated in fp32 in channel order.  Weights in the int8 kernel's transposed image
 // [C/16][1024][16 B].
 // A CTA handles kE4m3Imgs images and one of kE4m3OSplit slices of the outputs (as gap_fc_kernel: the FC weights a CTA
-// streams from L2, and their E4M3 -> float decoding, then serve every image of the CTA).  The FP32 sums keep the
-// oracle's order (pixels in raster order, channels k = 0..C-1), so the result does not depend on the decomposition.
+// streams from L2, and their E4M3 -> float decoding, then serve every image of the CTA).  Every FP32 sum runs in one
+// fixed order (pixels in raster order, channels k = 0..C-1): an image's logits do not depend on the batch it is in,
+// on its neighbour in the CTA or on the output split (QUANT_SPEC 6 states the tolerance against the oracle's double sums).
 constexpr int kE4m3Imgs = 2;      // (the FC loop below is written for two)
 constexpr int kE4m3OSplit = 2;
 __global__ void __launch_bounds__(512)

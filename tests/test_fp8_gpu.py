@@ -161,3 +161,28 @@ def test_fp8_results_do_not_depend_on_timing():
         assert all(np.array_equal(outs[0], o) for o in outs[1:]), n
         m.close()
     ctx.close()
+
+
+def test_fp8_logits_do_not_depend_on_the_batch():
+    """the E4M3 GAP+FC tail pairs images per CTA and splits the outputs over two CTAs: an image's logits must be the
+    same bits whatever batch it arrives in (odd batches leave one CTA with a single image)"""
+    import torch
+    import dlq_b200
+    from dlq_b200 import synth
+    w = synth.make_weights(0)
+    s8 = orc.fp8_act_scales(synth.load_act_scales(0))
+    x = synth.make_input(2, 5)
+    ctx = dlq_b200.Context(0)
+    m = dlq_b200.ResNet18(ctx, w, s8, 5, fp8=True)
+    outs = {}
+    for n in (1, 2, 3, 5):
+        dl = torch.empty((n, 1000), dtype=torch.float32, device="cuda")
+        m.forward(torch.from_numpy(np.ascontiguousarray(x[:n])).cuda(), dl)
+        ctx.sync()
+        outs[n] = dl.cpu().numpy()
+    for n in (1, 2, 3):
+        assert np.array_equal(outs[n], outs[5][:n]), n
+    assert np.isfinite(outs[5]).all()
+    m.close()
+    ctx.close()
+
