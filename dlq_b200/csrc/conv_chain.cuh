@@ -1,4 +1,5 @@
-// conv_chain.cuh — ONE persistent kernel running a sequence of convolution layers (ResNet-18's layer3 / layer4 blocks).
+// conv_chain.cuh — ONE persistent kernel running a sequence of convolution layers (ResNet-18: layer1's four convs as one
+// chain of single CTAs, the fifteen convs of layer2 .. layer4 as one chain of CTA pairs).
 //
 // Why: with one launch per layer, every SM pays, per layer, the hand-over from one CTA to the next - the last item's
 // epilogue drains with the tensor pipe idle, the CTA exits, the next one is scheduled, allocates TMEM, initialises
