@@ -301,6 +301,18 @@ int plan_conv(dlq_ctx* ctx, const dlq_conv_weights* w, const Act& in, const Act&
   const uint32_t b_stage_bytes = (p.step_bytes + 1023u) & ~1023u;
   int MT = std::max(1, 256 / p.n_tile);
   if (w->fused) MT = 1;      // two accumulator blocks per tile: 2 * n_tile columns per stage
+  // Small problems (the latency configurations): fewer tiles per item while the items do not fill the SMs - an item's MMAs
+  // and its epilogue are serial inside a CTA, so more and smaller items shorten the layer (batch 1: 8.5 -> ~6 us per
+  // layer1 conv).  Chain members keep the chain's static tile shape.
+  if (allow_resident && !w->fused) {
+    const long long last = (static_cast<long long>(in.N - 1) * p.Pv + (p.Ho - 1)) * p.Wp + (p.Wo - 1);
+    while (MT > 1) {
+      const int ss = p.two ? ((MT * kTileM) / p.Wp) * p.Wp : MT * kTileM;
+      const long long items = ((last / ss + 1 + ncta - 1) / ncta) * n_tiles;
+      if (items >= ctx->num_sms / ncta) break;
+      MT >>= 1;
+    }
+  }
   if (const char* e = dlq_dbg_env("DLQ_DBG_MT")) { const int v = atoi(e); if ((v == 1 || v == 2 || v == 4) && v * p.n_tile <= 512) MT = v; }
   int NR = 0;
   const size_t all_b = static_cast<size_t>(p.n_steps) * b_stage_bytes;

@@ -632,9 +632,9 @@ int build_plan(dlq_resnet18* m, int N, dlq_resnet18::Plan* P) {
   int units = 0;
   auto keep = [&](int i) {
     ConvLaunch& L = P->L[i];
+    if (!(m->tile_flags || in_chain(i))) return;      // (no consumer waits on this conv tile by tile)
     const int n = conv_flag_units(L);
-    if (m->d_flags && (m->tile_flags || in_chain(i)) && units + n <= m->n_flags)
-      conv_set_flags(&L, m->d_flags + units, m->d_flags + m->n_flags);
+    if (m->d_flags && units + n <= m->n_flags) conv_set_flags(&L, m->d_flags + units, m->d_flags + m->n_flags);
     units += n;
   };
   for (int b = 0; b < 8; ++b) {
@@ -859,7 +859,15 @@ int dlq_resnet18_create(dlq_ctx* ctx, const dlq_resnet18_weights* w, int max_bat
   rc = build_plan(m.get(), N, P.get());
   if (rc != DLQ_OK) return rc;
   {
-    m->n_flags = P->flag_units;
+    // (room for every option setting at every batch <= max_batch: with "tile_flags" all twenty convs keep counters, and
+    // small batches are planned with down to a quarter of the positions per unit)
+    std::unique_ptr<dlq_resnet18::Plan> Pall(new dlq_resnet18::Plan());
+    const bool tf = m->tile_flags;
+    m->tile_flags = true;
+    rc = build_plan(m.get(), N, Pall.get());
+    m->tile_flags = tf;
+    if (rc != DLQ_OK) return rc;
+    m->n_flags = 4 * std::max(P->flag_units, Pall->flag_units) + 1024;
     void* p = nullptr;
     DLQ_CUDA(ctx, cudaMalloc(&p, (static_cast<size_t>(m->n_flags) + 1) * sizeof(unsigned int)));
     m->allocs.push_back(p);

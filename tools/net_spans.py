@@ -22,7 +22,7 @@ def main():
     ctx = dlq_b200.Context(0)
     B = a.batch
     weights, scales = synth.make_weights(0), synth.load_act_scales(0)
-    x = torch.from_numpy(np.tile(synth.make_input(0, 2), (B // 2, 1, 1, 1))).cuda()
+    x = torch.from_numpy(np.tile(synth.make_input(0, 2), ((B + 1) // 2, 1, 1, 1))[:B].copy()).cuda()
     logits = torch.empty((B, 1000), dtype=torch.float32, device="cuda")
     out = {}
     for name, fp8 in (("int8", False), ("e4m3", True)):
