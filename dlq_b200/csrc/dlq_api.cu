@@ -494,8 +494,9 @@ struct dlq_resnet18 {
   int n_flags = 0;
   bool flags_dirty = false;   // a forward failed half-way: clear the counters before the next one
   bool conv_chain = true;     // batches above kFuseMaxBatch: the blocks from chain_first_block on as one persistent launch
-  int chain_min_batch = 17;   // smallest batch planned with chains (option "chain_min_batch"); below it: one launch per conv,
-                              // shortcut convs fused into conv1
+  int chain_min_batch = 40;   // smallest batch planned with chains (option "chain_min_batch"); below it: one launch per conv
+                              // with tile shapes picked for the problem size (measured per forward, chains vs separate launches:
+                              // batch 17: 208 vs 182 us, 32: 235 vs 229, 48: 260 vs 276, 64: 280 vs 299, 96: 335 vs 382)
   int chain_mode0 = 0;        // first launch mode new plans try for the chain (launch_chain; option "chain_launch_mode")
   bool chain_l1 = true;       // layer1's four convs as a chain of their own (option "chain_layer1")
   int chain_start = 7;        // conv index of the main chain's first member: conv1 (1 + 3b) or conv2 (2 + 3b) of a block;

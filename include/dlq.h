@@ -244,15 +244,16 @@ int dlq_resnet18_submit_host_u8(dlq_resnet18* m, const uint8_t* x_hwc_host, int 
 int dlq_resnet18_wait(dlq_resnet18* m);
 /* profile slots of one forward (dlq_resnet18_profile / _read_stamps): 23 = quantise, 20 convs, max-pool, GAP+FC */
 int dlq_resnet18_launches(const dlq_resnet18* m);
-/* kernels a forward of batch N really launches: 6 above batch 16 (quantise, stem conv, max-pool, the layer1 chain, the
- * layer2..4 chain, GAP+FC), 20 at batch <= 16 (the three 1x1 shortcut convs ride on conv1's launch), 23 with the chains
- * switched off */
+/* kernels a forward of batch N really launches: 6 from batch 40 on (quantise, stem conv, max-pool, the layer1 chain, the
+ * layer2..4 chain, GAP+FC), 20 at batch <= 16 (the three 1x1 shortcut convs ride on conv1's launch), 23 in between and
+ * with the chains switched off */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
 /* Plan options (A/B measurements and tools; results are bit-identical whatever their values).  Synchronises, drops the
  * cached plans and any captured graph.
  *   "conv_chain" (1)        layer1's four convs and the fifteen convs of layer2..4 as two persistent cooperative launches
  *                           (csrc/conv_chain.cuh) for batches >= "chain_min_batch"; 0: one launch per conv
- *   "chain_min_batch" (17)  smallest batch planned with chains (measured: at batch 1 they cost 202 vs 186 us per forward)
+ *   "chain_min_batch" (40)  smallest batch planned with chains (measured per forward, chains vs separate launches: batch 32
+ *                           235 vs 229 us, batch 48 260 vs 276 us)
  *   "chain_layer1" (1), "chain_start" (7) / "chain_first_block"   which convs the chains cover
  *   "chain_launch_mode" (0) 0 cooperative + programmatic stream serialization, 1 cooperative, 2 neither (profilers)
  *   "tile_flags" (0)        also between SEPARATE conv launches: consumers wait for the completion counters of the producer

@@ -42,9 +42,10 @@ def _forward(ctx, m, x):
 
 @pytest.mark.parametrize("n", [1, 3, 17, 40])
 def test_network_matches_oracle(ctx, model256, n):
-    """n <= 16 runs the fused-shortcut plan (conv1 + 1x1/s2 in one launch, K-split issuers); n = 17 and 40 run the plan
-    the benchmark runs at batch 256 - separate 3x3/s2 and 1x1/s2 kernels reading parity-plane tensors - on DISTINCT
-    images, all six int8 checkpoints and the logits"""
+    """n <= 16 runs the fused-shortcut plan (conv1 + 1x1/s2 in one launch, K-split issuers); n = 17 the un-fused plan with
+    one launch per conv (separate 3x3/s2 and 1x1/s2 kernels reading parity-plane tensors, tile shapes picked for the
+    problem size); n = 40 the plan the benchmark runs at batch 256 (the two conv chains) - on DISTINCT images, all six int8
+    checkpoints and the logits"""
     w = synth.make_weights(0)
     x = synth.make_input(7, n)
     assert len({x[i].tobytes() for i in range(n)}) == n
@@ -208,13 +209,17 @@ def test_launch_count_and_span_stamps(ctx, model256):
     import torch
     assert model256.launches == 23
     assert model256.launches_for_batch(8) == 20 and model256.launches_for_batch(16) == 20
-    # above 16: layer1's four convs share one persistent launch, the fifteen convs of layer2..4 another (conv_chain.cuh)
-    assert model256.launches_for_batch(17) == 6 and model256.launches_for_batch(256) == 6
+    # from batch 40 on: layer1's four convs share one persistent launch, the fifteen convs of layer2..4 another (conv_chain.cuh)
+    assert model256.launches_for_batch(17) == 23 and model256.launches_for_batch(39) == 23
+    assert model256.launches_for_batch(40) == 6 and model256.launches_for_batch(256) == 6
     assert model256.plan_info(256, "chain_layers") == 19 and model256.plan_info(256, "chains") == 2
     assert model256.plan_info(8, "chain_layers") == 0
     model256.set_option("conv_chain", 0)
-    assert model256.launches_for_batch(17) == 23 and model256.launches_for_batch(256) == 23
+    assert model256.launches_for_batch(40) == 23 and model256.launches_for_batch(256) == 23
     model256.set_option("conv_chain", 1)
+    model256.set_option("chain_min_batch", 17)
+    assert model256.launches_for_batch(17) == 6
+    model256.set_option("chain_min_batch", 40)
     x = torch.from_numpy(synth.make_input(0, 32)).cuda()
     dl = torch.empty((32, 1000), dtype=torch.float32, device="cuda")
     model256.enable_stamps(4)
@@ -289,6 +294,7 @@ def test_conv_chain_equals_separate_launches(ctx, n, start):
     import torch
     import dlq_b200
     m = dlq_b200.ResNet18(ctx, synth.make_weights(0), synth.load_act_scales(0), n)
+    m.set_option("chain_min_batch", 17)     # (default 40: these cases exercise the chains on small batches)
     m.set_option("chain_start", start)      # 7 = layer2.0.conv1 (default), 8 = layer2.0.conv2, 19 = layer4.0.conv1, 13 = layer3.0.conv1, ...
     m.set_option("chain_layer1", 0 if start == 13 else 1)
     x = _tile(synth.make_input(17, min(n, 40)), n)
