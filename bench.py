@@ -533,7 +533,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         rng_u8 = np.random.default_rng(rank)
         uh = torch.from_numpy(rng_u8.integers(0, 256, (B, 224, 224, 3), dtype=np.uint8)).pin_memory()
         st, fin = pipe(lambda: model.submit_host_u8(uh, lh))
-        ms_u8 = timed_wall(st, e2e_steps, 3, fin)
+        ms_u8_trials = sorted(timed_wall(st, e2e_steps, 3, fin) for _ in range(3))
+        ms_u8 = ms_u8_trials[1]          # median of three trials: this number moves with the host side of the box
         du = uh.cuda()
         lu = torch.empty((B, 1000), dtype=torch.float32, device="cuda")
         torch.cuda.synchronize()
@@ -542,8 +543,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         e2e_u8 = {"value": B * world * e2e_steps / (ms_u8 * 1e-3), "unit": "images/s",
                   "h2d_bytes_per_step": int(uh.numel()) * world, "d2h_bytes_per_step": int(lh.numel() * 4) * world,
                   "logits_verified": bool(torch.equal(lh.view(torch.int32), lu.cpu().view(torch.int32))),
+                  "trials_ms_per_step": [round(t / e2e_steps, 4) for t in ms_u8_trials],
                   "note": "pinned host uint8 HWC images -> H2D -> normalise+quantise+forward -> D2H logits; pipelined "
-                          "(dlq_resnet18_submit_host_u8 / _wait: copy of batch k+1 under the forward of batch k)"}
+                          "(dlq_resnet18_submit_host_u8 / _wait: copy of batch k+1 under the forward of batch k); median of "
+                          "three trials"}
         del du, lu
     except Exception as ex:
         e2e_u8 = {"value": None, "error": str(ex)}
