@@ -568,7 +568,8 @@ inline int act_c1(int b) { return 2 + 3 * b; }
 inline int act_ds(int b) { return 3 + 3 * b; }
 inline int act_out(int b) { return 4 + 3 * b; }
 constexpr int kActInput = 0, kActStem = 1, kActGap = 26;
-constexpr int kFuseMaxBatch = 16;
+constexpr int kFuseMaxBatch = 39;      // shortcut convs ride on conv1's launch up to this batch (measured per forward, fused vs
+                                       // separate: batch 17: 175 vs 182 us, 32: 219 vs 229; equal at batch 256)
 
 int build_plan_without_chain(dlq_resnet18* m, int N, dlq_resnet18::Plan* P);
 
@@ -889,7 +890,7 @@ int dlq_resnet18_launches(const dlq_resnet18* m) {
   (void)m;
   return 1 /*quantise+s2d*/ + 20 /*convs*/ + 1 /*max-pool*/ + 1 /*GAP+FC*/;
 }
-/* kernels one forward of batch N really launches: 23, or 20 when the shortcut convs are fused into conv1 (N <= 16) */
+/* kernels one forward of batch N really launches: 6 with the conv chains (N >= 40), 20 with the shortcut convs fused into conv1 (N < 40), else 23 */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N) {
   if (!m || N <= 0) return 0;
   int fused = 0;

@@ -245,8 +245,8 @@ int dlq_resnet18_wait(dlq_resnet18* m);
 /* profile slots of one forward (dlq_resnet18_profile / _read_stamps): 23 = quantise, 20 convs, max-pool, GAP+FC */
 int dlq_resnet18_launches(const dlq_resnet18* m);
 /* kernels a forward of batch N really launches: 6 from batch 40 on (quantise, stem conv, max-pool, the layer1 chain, the
- * layer2..4 chain, GAP+FC), 20 at batch <= 16 (the three 1x1 shortcut convs ride on conv1's launch), 23 in between and
- * with the chains switched off */
+ * layer2..4 chain, GAP+FC), 20 below (the three 1x1 shortcut convs ride on conv1's launch), 23 from batch 40 on with the
+ * chains switched off */
 int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
 /* Plan options (A/B measurements and tools; results are bit-identical whatever their values).  Synchronises, drops the
  * cached plans and any captured graph.
@@ -259,14 +259,15 @@ int dlq_resnet18_launches_for_batch(const dlq_resnet18* m, int N);
  *   "tile_flags" (0)        also between SEPARATE conv launches: consumers wait for the completion counters of the producer
  *                           units their rows touch instead of for the producer's grid (griddepcontrol.wait) */
 int dlq_resnet18_set_option(dlq_resnet18* m, const char* key, int value);
-/* Further keys: "conv_chain" (default 1): at batches above 16 the convs from "chain_start" to the last one run as ONE
- * persistent cooperative kernel (csrc/conv_chain.cuh) whose CTA pairs walk the layers without leaving the SMs - no
- * per-layer hand-over, no partial last waves - with the tile-level dependency flags between them.  "chain_start" is the
- * conv index (DLQ_NUM_CONVS numbering) of a block's conv1 or conv2; default 8 = layer2.0.conv2, the first of the thirteen
- * convs with 128 or more input channels; "chain_first_block" = b is shorthand for conv1 of block b (1..7).  A chain whose
- * layers do not share the kernel's static tile configuration falls back to one launch per conv.  Bit-identical results. */
+/* "conv_chain" in detail: from batch "chain_min_batch" on, the convs from "chain_start" to the last one run as ONE persistent
+ * cooperative kernel (csrc/conv_chain.cuh) whose CTA pairs walk the layers without leaving the SMs - no per-layer
+ * hand-over, no partial last waves - with the tile-level dependency flags between them, and layer1's four convs as a
+ * second one ("chain_layer1").  "chain_start" is the conv index (DLQ_NUM_CONVS numbering) of a block's conv1 or conv2;
+ * default 7 = layer2.0.conv1, i.e. the fifteen convs of layer2..4; "chain_first_block" = b is shorthand for conv1 of block
+ * b (1..7).  A chain whose layers do not share the kernel's static tile configuration falls back to one launch per
+ * conv.  Bit-identical results. */
 /* facts about the launch plan of batch N (planned on demand): "chain_layers" (0 = one launch per conv), "chain_launch_mode",
- * "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units" */
+ * "chain_cta_pairs", "chain_a_stages", "chain_b_stages", "flag_units", "chains" */
 int dlq_resnet18_plan_info(dlq_resnet18* m, int N, const char* key, int* value);
 /* dependency waits that ran into the 4 s safety timeout since creation (must be 0).  Synchronises. */
 int dlq_resnet18_dep_timeouts(dlq_resnet18* m, unsigned int* count);
