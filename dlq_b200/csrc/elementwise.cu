@@ -364,30 +364,24 @@ gap_fc_e4m3_kernel(const int8_t* __restrict__ in, int N, int H, int W, int C, in
   // the last conv grid has completed: clear this forward's dependency counters for the next one (as gap_fc_kernel)
   for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x; i < n_zero; i += gridDim.x * gridDim.y * blockDim.x)
     zero[i] = 0u;
-  // GAP: thread = (image, 16-channel group); the pixels' 16-byte loads are independent (seven in flight), the FP32
-  // additions of a channel stay in raster order
-  const int cv = C / 16;
-  for (int i = threadIdx.x; i < nimg * cv; i += blockDim.x) {
-    const int im = i / cv, cg = i - im * cv;
+  // GAP: thread = (image, channel); the pixels' byte loads are independent (sixteen in flight, a warp reads 32 consecutive
+  // bytes per pixel), the FP32 additions of a channel stay in raster order (out-of-range slots add +0.0: no change)
+  for (int i = threadIdx.x; i < nimg * C; i += blockDim.x) {
+    const int im = i / C, c = i - im * C;
     const uint8_t* src = reinterpret_cast<const uint8_t*>(in) +
-                         (static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR)) * W * C + cg * 16;
-    float s[16];
+                         (static_cast<size_t>(PR) + static_cast<size_t>(n0 + im) * (H + PR)) * W * C + c;
+    const int HW = H * W;
+    float s = 0.f;
+    for (int p0 = 0; p0 < HW; p0 += 16) {
+      uint8_t v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) s[j] = 0.f;
-#pragma unroll 7
-    for (int px = 0; px < H * W; ++px) {
-      const int4 v = __ldg(reinterpret_cast<const int4*>(src + static_cast<size_t>(px) * C));
-      const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+      for (int j = 0; j < 16; ++j) v[j] = p0 + j < HW ? __ldg(src + static_cast<size_t>(p0 + j) * C) : static_cast<uint8_t>(0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) s[j] = __fadd_rn(s[j], e4m3_to_float(static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)))));
+      for (int j = 0; j < 16; ++j) s = __fadd_rn(s, e4m3_to_float(v[j]));
     }
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int c = cg * 16 + j;
-      const uint8_t q = float_to_e4m3(__fmul_rn(__fmul_rn(s[j], scale_over_hw), inv_gap_scale));
-      if (gap_q && blockIdx.y == 0) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
-      gq_s[c * kE4m3Imgs + im] = e4m3_to_float(q);      // [C][imgs]: one shared load per channel serves the CTA's images
-    }
+    const uint8_t q = float_to_e4m3(__fmul_rn(__fmul_rn(s, scale_over_hw), inv_gap_scale));
+    if (gap_q && blockIdx.y == 0) gap_q[static_cast<size_t>(n0 + im) * C + c] = static_cast<int8_t>(q);
+    gq_s[c * kE4m3Imgs + im] = e4m3_to_float(q);      // [C][imgs]: one shared load per channel serves the CTA's images
   }
   if (nimg < kE4m3Imgs)
     for (int c = threadIdx.x; c < C; c += blockDim.x) gq_s[c * kE4m3Imgs + kE4m3Imgs - 1] = 0.f;     // (odd batch: unused slot)
