@@ -602,7 +602,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                         "dtype": "e4m3 x e4m3 -> f32 (tcgen05 kind::f8f6f4)", "batch_per_gpu": B,
                         "vs_int8": (B * world * n8 / (ms8 * 1e-3)) / value,
                         "why_slower": "same kernels and tile shapes (tools/net_spans.py): layer1-2 equal, every layer3 / layer4 "
-                                      "conv 4-6 us longer (the tensor-bound layers: kind::f8f6f4 with FP32 accumulators), and "
+                                      "conv 4-6 us longer (the tensor-bound layers; a tight-loop probe issues kind::f8f6f4 and kind::i8 pair MMAs at the same "
+                                      "rate, so the cause is not the MMA rate itself and was not isolated), and "
                                       "the GAP+FC tail 16 us longer (FP32 sums in the oracle's sequential order, E4M3 weights "
                                       "decoded per use, where the int8 tail is dp4a)"}
             m8.close()
